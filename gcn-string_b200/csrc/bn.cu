@@ -1,0 +1,372 @@
+// K2 / K8 — Keras BatchNormalization (rank-2, non-fused path) + PReLU, forward and backward.
+//
+// Upstream semantics restated (reference instantiates them through
+// GeneralGNN at src/scripts/gcn.py:320 and runs them at :334 training / :351 inference):
+//   training:  mean = reduce_mean(h, 0); var = reduce_mean((h - mean)^2, 0)   (biased, two-pass)
+//              y = h * inv + (beta - mean * inv),  inv = gamma * rsqrt(var + eps)
+//              moving <- moving - (moving - batch) * (1 - momentum)
+//   inference: the same formula with the moving statistics
+//   PReLU:     f(z) = relu(z) - alpha * relu(-z), alpha per channel; df/dz = 1 (z>0), alpha
+//              (z<0), 0 (z==0); df/dalpha = min(z, 0)
+// The column reductions run ONE pass over h with fp64 accumulators (sum, sum of squares):
+// in fp64 E[h^2] - mean^2 reproduces the two-pass variance to fp32 rounding.  Partials are
+// written per row-split and combined in a fixed order: deterministic, no atomics.
+#include "common.cuh"
+
+namespace gcs {
+
+constexpr int kBnThreads = 256;   // 32 column lanes x 8 row warps
+
+struct BnGrid {
+  int vec;         // 4 or 1 columns per lane
+  int col_blocks;  // grid.x
+  int splits;      // grid.y
+  int64_t rows_per_split;
+};
+
+static BnGrid bn_grid(int64_t M, int C, bool vec_ok) {
+  BnGrid g;
+  g.vec = vec_ok ? 4 : 1;
+  g.col_blocks = static_cast<int>(ceil_div(C, 32 * g.vec));
+  int64_t target = 4LL * sm_count();
+  int64_t s = ceil_div(target, g.col_blocks);
+  int64_t max_s = ceil_div(M, 32);
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 65535) s = 65535;
+  g.rows_per_split = ceil_div(M > 0 ? M : 1, s);
+  g.splits = static_cast<int>(ceil_div(M > 0 ? M : 1, g.rows_per_split));
+  return g;
+}
+
+// Upper bound on splits for workspace sizing (alignment-independent).
+static int64_t bn_max_splits(int64_t M) {
+  int64_t s = 4LL * sm_count();
+  int64_t max_s = ceil_div(M > 0 ? M : 1, 32);
+  return s < max_s ? s : max_s;
+}
+
+// Block-level combine of per-warp fp64 partials: warps 1..7 park their values in shared
+// memory, warp 0 adds them in warp order and writes the split's partial.
+template <int NV>
+__device__ __forceinline__ void block_store_partials(double (&v)[NV], double* __restrict__ dst_col0,
+                                                     int64_t col_stride, int ncols_valid, bool lane_valid) {
+  __shared__ double sm[7][32][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp > 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sm[warp - 1][lane][k] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0 && lane_valid) {
+#pragma unroll
+    for (int w = 0; w < 7; ++w)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) v[k] += sm[w][lane][k];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) dst_col0[k] = v[k];
+  }
+  (void)col_stride; (void)ncols_valid;
+}
+
+// partial layout: ws[(split * C + c) * Q + q], Q quantities per column.
+template <int VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(
+    const float* __restrict__ h, int64_t ldh, int64_t M, int C, int64_t rows_per_split,
+    double* __restrict__ ws) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + lane) * VEC;
+  const int64_t rb = blockIdx.y * rows_per_split;
+  int64_t re = rb + rows_per_split;
+  if (re > M) re = M;
+  double acc[2 * VEC];
+#pragma unroll
+  for (int k = 0; k < 2 * VEC; ++k) acc[k] = 0.0;
+  if (c < C) {
+    for (int64_t r = rb + warp; r < re; r += 8) {
+      float v[VEC];
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        v[0] = __ldg(h + r * ldh + c);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const double d = static_cast<double>(v[k]);
+        acc[2 * k] += d;
+        acc[2 * k + 1] = fma(d, d, acc[2 * k + 1]);
+      }
+    }
+  }
+  block_store_partials<2 * VEC>(acc, ws + (static_cast<int64_t>(blockIdx.y) * C + c) * 2, 0, 0, c < C);
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
+                                      float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < splits; ++k) {
+    s += ws[(static_cast<int64_t>(k) * C + c) * 2];
+    q += ws[(static_cast<int64_t>(k) * C + c) * 2 + 1];
+  }
+  const double m = s / static_cast<double>(M);
+  double v = q / static_cast<double>(M) - m * m;
+  if (v < 0.0) v = 0.0;
+  mean[c] = static_cast<float>(m);
+  var[c] = static_cast<float>(v);
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               float eps, float momentum, float* __restrict__ moving_mean,
+                               float* __restrict__ moving_var, float* __restrict__ scale,
+                               float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = mean[c], v = var[c];
+  const float inv = gamma[c] * __frsqrt_rn(v + eps);
+  scale[c] = inv;
+  shift[c] = beta[c] - m * inv;
+  if (moving_mean) {
+    const float decay = 1.0f - momentum;
+    moving_mean[c] = moving_mean[c] - (moving_mean[c] - m) * decay;
+    moving_var[c] = moving_var[c] - (moving_var[c] - v) * decay;
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_prelu_fwd_kernel(
+    const float* __restrict__ h, int64_t ldh, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ alpha, float* __restrict__ out,
+    int64_t ldo, int64_t M, int C) {
+  const int cpr = (C + VEC - 1) / VEC;   // column groups per row
+  const int64_t total = M * cpr;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / cpr;
+    const int c = static_cast<int>(idx - r * cpr) * VEC;
+    if (VEC == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+      if (alpha) {
+        const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + c));
+        v.x = bn_prelu(v.x, sc.x, sh.x, al.x); v.y = bn_prelu(v.y, sc.y, sh.y, al.y);
+        v.z = bn_prelu(v.z, sc.z, sh.z, al.z); v.w = bn_prelu(v.w, sc.w, sh.w, al.w);
+      } else {
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+      }
+      *reinterpret_cast<float4*>(out + r * ldo + c) = v;
+    } else {
+      const float z = fmaf(__ldg(h + r * ldh + c), __ldg(scale + c), __ldg(shift + c));
+      out[r * ldo + c] = alpha ? (z > 0.f ? z : __ldg(alpha + c) * z) : z;
+    }
+  }
+}
+
+// Backward pass 1: per column S1 = sum dz, S2 = sum dz*xhat, S3 = sum da*min(z,0), with
+// z = gamma*xhat + beta, dz = da * slope(z).
+template <int VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(
+    const float* __restrict__ da, int64_t ldda, const float* __restrict__ h, int64_t ldh,
+    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ alpha, float eps, int64_t M, int C,
+    int64_t rows_per_split, double* __restrict__ ws) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + lane) * VEC;
+  const int64_t rb = blockIdx.y * rows_per_split;
+  int64_t re = rb + rows_per_split;
+  if (re > M) re = M;
+  double acc[3 * VEC];
+#pragma unroll
+  for (int k = 0; k < 3 * VEC; ++k) acc[k] = 0.0;
+  if (c < C) {
+    float mu[VEC], rs[VEC], ga[VEC], be[VEC], al[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      mu[k] = __ldg(mean + c + k);
+      rs[k] = __frsqrt_rn(__ldg(var + c + k) + eps);
+      ga[k] = __ldg(gamma + c + k);
+      be[k] = __ldg(beta + c + k);
+      al[k] = alpha ? __ldg(alpha + c + k) : 1.f;
+    }
+    for (int64_t r = rb + warp; r < re; r += 8) {
+      float hv[VEC], gv[VEC];
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(da + r * ldda + c));
+        hv[0] = t.x; hv[1] = t.y; hv[2] = t.z; hv[3] = t.w;
+        gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
+      } else {
+        hv[0] = __ldg(h + r * ldh + c);
+        gv[0] = __ldg(da + r * ldda + c);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float xhat = (hv[k] - mu[k]) * rs[k];
+        const float z = fmaf(ga[k], xhat, be[k]);
+        float dz = gv[k];
+        if (alpha) {
+          dz = z > 0.f ? gv[k] : (z < 0.f ? gv[k] * al[k] : 0.f);
+          acc[3 * k + 2] += static_cast<double>(gv[k] * fminf(z, 0.f));
+        }
+        acc[3 * k] += static_cast<double>(dz);
+        acc[3 * k + 1] = fma(static_cast<double>(dz), static_cast<double>(xhat), acc[3 * k + 1]);
+      }
+    }
+  }
+  block_store_partials<3 * VEC>(acc, ws + (static_cast<int64_t>(blockIdx.y) * C + c) * 3, 0, 0, c < C);
+}
+
+// coef[c] = {S1/M, S2/M} as floats for the apply pass; dgamma/dbeta/dalpha written here.
+__global__ void bn_bwd_final_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ dalpha, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int k = 0; k < splits; ++k) {
+    const double* p = ws + (static_cast<int64_t>(k) * C + c) * 3;
+    s1 += p[0]; s2 += p[1]; s3 += p[2];
+  }
+  if (dbeta) dbeta[c] = static_cast<float>(s1);
+  if (dgamma) dgamma[c] = static_cast<float>(s2);
+  if (dalpha) dalpha[c] = static_cast<float>(s3);
+  coef[2 * c] = static_cast<float>(s1 / static_cast<double>(M));
+  coef[2 * c + 1] = static_cast<float>(s2 / static_cast<double>(M));
+}
+
+// Backward pass 2: dh = gamma*rstd*(dz - S1/M - xhat*S2/M).
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    const float* __restrict__ da, int64_t ldda, const float* __restrict__ h, int64_t ldh,
+    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ alpha, float eps,
+    const float* __restrict__ coef, float* __restrict__ dh, int64_t lddh, int64_t M, int C) {
+  const int cpr = (C + VEC - 1) / VEC;
+  const int64_t total = M * cpr;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / cpr;
+    const int c = static_cast<int>(idx - r * cpr) * VEC;
+    float hv[VEC], gv[VEC], o[VEC];
+    if (VEC == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
+      const float4 u = __ldg(reinterpret_cast<const float4*>(da + r * ldda + c));
+      hv[0] = t.x; hv[1] = t.y; hv[2] = t.z; hv[3] = t.w;
+      gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
+    } else {
+      hv[0] = __ldg(h + r * ldh + c);
+      gv[0] = __ldg(da + r * ldda + c);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float mu = __ldg(mean + c + k), rs = __frsqrt_rn(__ldg(var + c + k) + eps);
+      const float ga = __ldg(gamma + c + k), be = __ldg(beta + c + k);
+      const float xhat = (hv[k] - mu) * rs;
+      const float z = fmaf(ga, xhat, be);
+      float dz = gv[k];
+      if (alpha) {
+        const float al = __ldg(alpha + c + k);
+        dz = z > 0.f ? gv[k] : (z < 0.f ? gv[k] * al : 0.f);
+      }
+      o[k] = ga * rs * (dz - __ldg(coef + 2 * (c + k)) - xhat * __ldg(coef + 2 * (c + k) + 1));
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(dh + r * lddh + c) = make_float4(o[0], o[1], o[2], o[3]);
+    else dh[r * lddh + c] = o[0];
+  }
+}
+
+}  // namespace gcs
+
+using namespace gcs;
+
+static inline int64_t elementwise_blocks(int64_t work) {
+  int64_t b = ceil_div(work, 256);
+  const int64_t cap = 16LL * sm_count();
+  return b < 1 ? 1 : (b > cap ? cap : b);
+}
+
+extern "C" int64_t gcs_bn_workspace_bytes(int64_t M, int32_t C) {
+  if (M < 0 || C <= 0) return 0;
+  return round_up(bn_max_splits(M) * C * 3 * static_cast<int64_t>(sizeof(double)), 256) +
+         round_up(2LL * C * sizeof(float), 256);
+}
+
+extern "C" int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, float* mean, float* var,
+                            void* workspace, int64_t workspace_bytes, gcs_stream stream) {
+  GCS_CHECK_ARG(M > 0 && C > 0, "gcs_bn_stats: needs at least one row (M=%lld, C=%d)", (long long)M, C);
+  GCS_CHECK_ARG(h && mean && var && workspace && ldh >= C, "gcs_bn_stats: bad pointer / leading dimension");
+  if (workspace_bytes < gcs_bn_workspace_bytes(M, C))
+    return fail(GCS_ERR_WORKSPACE, "gcs_bn_stats: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)gcs_bn_workspace_bytes(M, C));
+  GCS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "gcs_bn_stats: workspace must be 8-byte aligned");
+  const bool vec = (C % 4 == 0) && (ldh % 4 == 0) && aligned16(h);
+  const BnGrid g = bn_grid(M, C, vec);
+  cudaStream_t st = as_stream(stream);
+  double* ws = static_cast<double*>(workspace);
+  dim3 grid(g.col_blocks, g.splits);
+  if (vec) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
+  else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
+  GCS_CHECK_LAUNCH("bn_stats_partial_kernel");
+  bn_stats_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, M, mean, var);
+  GCS_CHECK_LAUNCH("bn_stats_final_kernel");
+  return GCS_OK;
+}
+
+extern "C" int gcs_bn_fold(const float* mean, const float* var, const float* gamma, const float* beta,
+                           float eps, float momentum, float* moving_mean, float* moving_var, float* scale,
+                           float* shift, int32_t C, gcs_stream stream) {
+  GCS_CHECK_ARG(C > 0 && mean && var && gamma && beta && scale && shift, "gcs_bn_fold: bad argument");
+  GCS_CHECK_ARG((moving_mean != nullptr) == (moving_var != nullptr), "gcs_bn_fold: moving_mean/moving_var must both be set or both NULL");
+  bn_fold_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, as_stream(stream)>>>(mean, var, gamma, beta, eps, momentum, moving_mean, moving_var, scale, shift, C);
+  GCS_CHECK_LAUNCH("bn_fold_kernel");
+  return GCS_OK;
+}
+
+extern "C" int gcs_bn_prelu_fwd(const float* h, int64_t ldh, const float* scale, const float* shift,
+                                const float* alpha, float* out, int64_t ldo, int64_t M, int32_t C,
+                                gcs_stream stream) {
+  GCS_CHECK_ARG(M >= 0 && C > 0, "gcs_bn_prelu_fwd: bad size");
+  if (M == 0) return GCS_OK;
+  GCS_CHECK_ARG(h && scale && shift && out && ldh >= C && ldo >= C, "gcs_bn_prelu_fwd: bad pointer / leading dimension");
+  const bool vec = (C % 4 == 0) && (ldh % 4 == 0) && (ldo % 4 == 0) && aligned16(h) && aligned16(out) &&
+                   aligned16(scale) && aligned16(shift) && (!alpha || aligned16(alpha));
+  cudaStream_t st = as_stream(stream);
+  if (vec) bn_prelu_fwd_kernel<4><<<static_cast<unsigned>(elementwise_blocks(M * (C / 4))), 256, 0, st>>>(h, ldh, scale, shift, alpha, out, ldo, M, C);
+  else bn_prelu_fwd_kernel<1><<<static_cast<unsigned>(elementwise_blocks(M * C)), 256, 0, st>>>(h, ldh, scale, shift, alpha, out, ldo, M, C);
+  GCS_CHECK_LAUNCH("bn_prelu_fwd_kernel");
+  return GCS_OK;
+}
+
+extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh, const float* mean,
+                                const float* var, const float* gamma, const float* beta, const float* alpha,
+                                float eps, float* dh, int64_t lddh, float* dgamma, float* dbeta, float* dalpha,
+                                int64_t M, int32_t C, void* workspace, int64_t workspace_bytes, gcs_stream stream) {
+  GCS_CHECK_ARG(M > 0 && C > 0, "gcs_bn_prelu_bwd: needs at least one row");
+  GCS_CHECK_ARG(da && h && mean && var && gamma && beta && dh && workspace, "gcs_bn_prelu_bwd: null pointer");
+  GCS_CHECK_ARG(ldda >= C && ldh >= C && lddh >= C, "gcs_bn_prelu_bwd: leading dimension smaller than C");
+  GCS_CHECK_ARG(!dalpha || alpha, "gcs_bn_prelu_bwd: dalpha requested without alpha");
+  if (workspace_bytes < gcs_bn_workspace_bytes(M, C))
+    return fail(GCS_ERR_WORKSPACE, "gcs_bn_prelu_bwd: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)gcs_bn_workspace_bytes(M, C));
+  GCS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "gcs_bn_prelu_bwd: workspace must be 8-byte aligned");
+  const bool vec = (C % 4 == 0) && (ldda % 4 == 0) && (ldh % 4 == 0) && (lddh % 4 == 0) && aligned16(da) &&
+                   aligned16(h) && aligned16(dh);
+  const BnGrid g = bn_grid(M, C, vec);
+  cudaStream_t st = as_stream(stream);
+  double* ws = static_cast<double*>(workspace);
+  float* coef = reinterpret_cast<float*>(static_cast<char*>(workspace) +
+                                         round_up(bn_max_splits(M) * C * 3 * static_cast<int64_t>(sizeof(double)), 256));
+  dim3 grid(g.col_blocks, g.splits);
+  if (vec) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
+  else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
+  GCS_CHECK_LAUNCH("bn_bwd_partial_kernel");
+  bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, M, dgamma, dbeta, dalpha, coef);
+  GCS_CHECK_LAUNCH("bn_bwd_final_kernel");
+  if (vec) bn_bwd_apply_kernel<4><<<static_cast<unsigned>(elementwise_blocks(M * (C / 4))), 256, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, coef, dh, lddh, M, C);
+  else bn_bwd_apply_kernel<1><<<static_cast<unsigned>(elementwise_blocks(M * C)), 256, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, coef, dh, lddh, M, C);
+  GCS_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  return GCS_OK;
+}

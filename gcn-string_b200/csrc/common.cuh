@@ -1,0 +1,57 @@
+// Shared helpers for the gcnstring_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/gcnstring_b200.h"
+
+namespace gcs {
+
+// Thread-local last-error string behind gcs_last_error().
+char* error_buffer();
+int fail(int status, const char* fmt, ...);
+
+inline cudaStream_t as_stream(gcs_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs on the current device (cached per device).
+int sm_count();
+
+#define GCS_CHECK_ARG(cond, ...)                                              \
+  do {                                                                        \
+    if (!(cond)) return ::gcs::fail(GCS_ERR_INVALID_ARGUMENT, __VA_ARGS__);   \
+  } while (0)
+
+#define GCS_CHECK_LAUNCH(name)                                                              \
+  do {                                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::gcs::fail(GCS_ERR_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define GCS_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::gcs::fail(GCS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));           \
+  } while (0)
+
+#define GCS_TRY(call)               \
+  do {                              \
+    int st__ = (call);              \
+    if (st__ != GCS_OK) return st__; \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// f(x) = prelu(x*scale + shift, alpha): the BatchNorm + PReLU prologue of GeneralConv.
+// Keras PReLU: relu(z) - alpha*relu(-z)  ->  z > 0 ? z : alpha*z.
+__device__ __forceinline__ float bn_prelu(float x, float sc, float sh, float al) {
+  float z = fmaf(x, sc, sh);
+  return z > 0.f ? z : al * z;
+}
+
+}  // namespace gcs

@@ -1,0 +1,319 @@
+// K1 / K9 — dense transforms on the CUDA cores (exact fp32 FFMA; the correctness anchor and
+// the path for widths below 128; the tcgen05 path in linear_tc.cu takes over above that).
+//
+// Replaces Keras Dense / K.dot + K.bias_add inside MLP and GeneralConv.call (SURVEY.md §8
+// a3/a4; reached from src/scripts/gcn.py:320,334) and their reverse-mode gradients
+// (gcn.py:337):   fwd  C = A.W + b        dW = A^T.dH, db = colsum(dH)       dA (+)= dH.W^T
+//
+// One tiled kernel computes  C[i,j] = sum_r P(i,r) Q(r,j)  for the three layouts:
+//   fwd        P = A  [I=M, R=K]  r-contiguous     Q = W  [R=K, J=N]  j-contiguous
+//   bwd_input  P = dH [I=M, R=N]  r-contiguous     Q = W  [J=K, R=N]  r-contiguous
+//   bwd_weight P = A  [R=M, I=K]  i-contiguous     Q = dH [R=M, J=N]  j-contiguous (split over R)
+// 128x128x16 tiles, 256 threads, 8x8 accumulators per thread (2x2 blocks of 4x4 so that
+// every shared-memory read is a conflict-free 128-bit load), register-prefetched double
+// buffering: one __syncthreads per 16-deep slice.
+#include "common.cuh"
+
+namespace gcs {
+
+constexpr int BT = 128;      // tile edge in i and j
+constexpr int BR = 16;       // reduction slice
+constexpr int PAD = 4;       // smem row padding (keeps 16 B alignment, halves store conflicts)
+constexpr int kGemmThreads = 256;
+
+// Operand tile loader.  RC = true: operand stored [X, R] row-major (reduction contiguous);
+// RC = false: stored [R, X] row-major (output dimension contiguous).  Each thread moves two
+// 4-element pieces per tile.
+template <bool RC, bool VEC>
+struct TileLoader {
+  float4 v[2];
+  __device__ __forceinline__ void load(const float* __restrict__ p, int64_t ld, int64_t x0, int64_t X,
+                                       int64_t r0, int64_t r_end) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int unit = t + u * kGemmThreads;
+      int64_t x, r;
+      if (RC) { x = x0 + unit / 4; r = r0 + (unit % 4) * 4; }
+      else    { r = r0 + unit / 32; x = x0 + (unit % 32) * 4; }
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (VEC) {
+        if (x < X && r < r_end)
+          val = __ldg(reinterpret_cast<const float4*>(RC ? p + x * ld + r : p + r * ld + x));
+      } else {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t xx = RC ? x : x + k, rr = RC ? r + k : r;
+          if (xx < X && rr < r_end) e[k] = __ldg(RC ? p + xx * ld + rr : p + rr * ld + xx);
+        }
+        val = make_float4(e[0], e[1], e[2], e[3]);
+      }
+      v[u] = val;
+    }
+  }
+  // smem tile layout: s[r][x], row stride BT + PAD
+  __device__ __forceinline__ void store(float* __restrict__ s) const {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int unit = t + u * kGemmThreads;
+      if (RC) {
+        const int x = unit / 4, r = (unit % 4) * 4;
+        s[(r + 0) * (BT + PAD) + x] = v[u].x;
+        s[(r + 1) * (BT + PAD) + x] = v[u].y;
+        s[(r + 2) * (BT + PAD) + x] = v[u].z;
+        s[(r + 3) * (BT + PAD) + x] = v[u].w;
+      } else {
+        const int r = unit / 32, x = (unit % 32) * 4;
+        *reinterpret_cast<float4*>(s + r * (BT + PAD) + x) = v[u];
+      }
+    }
+  }
+};
+
+// C (+)= P.Q (+ bias).  grid: (i tiles, j tiles, R splits); split z handles reduction range
+// [z*r_per_split, min(R, (z+1)*r_per_split)) and writes to C + z*c_split_stride.
+template <bool P_RC, bool Q_JC, bool VEC>
+__global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(
+    const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
+    float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int64_t I, int J, int64_t R,
+    int64_t r_per_split, int accumulate, int64_t c_split_stride) {
+  __shared__ __align__(16) float Ps[2][BR][BT + PAD];
+  __shared__ __align__(16) float Qs[2][BR][BT + PAD];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * BT;
+  const int j0 = blockIdx.y * BT;
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.z) * r_per_split;
+  int64_t r_end = r_begin + r_per_split;
+  if (r_end > R) r_end = R;
+  C += static_cast<int64_t>(blockIdx.z) * c_split_stride;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+
+  TileLoader<P_RC, VEC> lp;
+  TileLoader<!Q_JC, VEC> lq;
+  const int64_t n_slices = r_end > r_begin ? (r_end - r_begin + BR - 1) / BR : 0;
+  if (n_slices > 0) {
+    lp.load(P, ldp, i0, I, r_begin, r_end);
+    lq.load(Q, ldq, j0, J, r_begin, r_end);
+    lp.store(&Ps[0][0][0]);
+    lq.store(&Qs[0][0][0]);
+  }
+  __syncthreads();
+  for (int64_t s = 0; s < n_slices; ++s) {
+    const int cur = static_cast<int>(s & 1);
+    const bool more = s + 1 < n_slices;
+    if (more) {
+      lp.load(P, ldp, i0, I, r_begin + (s + 1) * BR, r_end);
+      lq.load(Q, ldq, j0, J, r_begin + (s + 1) * BR, r_end);
+    }
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&Ps[cur][r][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Ps[cur][r][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Qs[cur][r][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Qs[cur][r][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+    if (more) {
+      lp.store(&Ps[cur ^ 1][0][0]);
+      lq.store(&Qs[cur ^ 1][0][0]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    const int64_t i = i0 + (x < 4 ? ty * 4 + x : 64 + ty * 4 + (x - 4));
+    if (i >= I) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = j0 + half * 64 + tx * 4;
+      float* cp = C + i * ldc + j;
+      if (VEC) {
+        if (j < J) {
+          float4 o = make_float4(acc[x][half * 4], acc[x][half * 4 + 1], acc[x][half * 4 + 2], acc[x][half * 4 + 3]);
+          if (bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j));
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          }
+          if (accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(cp);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *reinterpret_cast<float4*>(cp) = o;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (j + k < J) {
+            float o = acc[x][half * 4 + k];
+            if (bias) o += __ldg(bias + j + k);
+            if (accumulate) o += cp[k];
+            cp[k] = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+// dW = sum over splits (fixed order), optional column sums for db handled separately.
+__global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restrict__ ws, int splits,
+                                                           int64_t n, float* __restrict__ out) {
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float s = ws[k];
+    for (int z = 1; z < splits; ++z) s += ws[static_cast<int64_t>(z) * n + k];
+    out[k] = s;
+  }
+}
+
+// db[j] = sum_m dH[m, j]: per-split column partials (fp32 within a split of <= a few
+// thousand rows, combined in fp64 in split order).
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dH, int64_t ldh,
+                                                             int64_t M, int N, int64_t rows_per_split,
+                                                             double* __restrict__ ws) {
+  __shared__ double sm[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int64_t rb = blockIdx.y * rows_per_split;
+  int64_t re = rb + rows_per_split;
+  if (re > M) re = M;
+  double acc = 0.0;
+  if (c < N)
+    for (int64_t r = rb + warp; r < re; r += 8) acc += static_cast<double>(__ldg(dH + r * ldh + c));
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < N) {
+    double s = sm[0][lane];
+    for (int w = 1; w < 8; ++w) s += sm[w][lane];
+    ws[static_cast<int64_t>(blockIdx.y) * N + c] = s;
+  }
+}
+
+__global__ void colsum_final_kernel(const double* __restrict__ ws, int splits, int N, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += ws[static_cast<int64_t>(z) * N + c];
+  db[c] = static_cast<float>(s);
+}
+
+struct WeightSplit {
+  int splits;
+  int64_t r_per_split;
+  int col_splits;
+  int64_t col_rows_per_split;
+};
+
+static WeightSplit weight_split(int64_t M, int K, int N) {
+  WeightSplit w;
+  const int64_t tiles = ceil_div(K, BT) * ceil_div(N, BT);
+  int64_t s = ceil_div(2LL * sm_count(), tiles);
+  const int64_t max_s = ceil_div(M > 0 ? M : 1, 4 * BR);
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  w.r_per_split = round_up(ceil_div(M > 0 ? M : 1, s), BR);
+  w.splits = static_cast<int>(ceil_div(M > 0 ? M : 1, w.r_per_split));
+  int64_t cs = ceil_div(2LL * sm_count(), ceil_div(N, 32));
+  const int64_t max_cs = ceil_div(M > 0 ? M : 1, 64);
+  if (cs > max_cs) cs = max_cs;
+  if (cs < 1) cs = 1;
+  w.col_rows_per_split = ceil_div(M > 0 ? M : 1, cs);
+  w.col_splits = static_cast<int>(ceil_div(M > 0 ? M : 1, w.col_rows_per_split));
+  return w;
+}
+
+}  // namespace gcs
+
+using namespace gcs;
+
+template <bool P_RC, bool Q_JC>
+static int launch_sgemm(const float* P, int64_t ldp, const float* Q, int64_t ldq, float* C, int64_t ldc,
+                        const float* bias, int64_t I, int J, int64_t R, int splits, int64_t r_per_split,
+                        int accumulate, int64_t c_split_stride, bool vec, cudaStream_t st, const char* who) {
+  const int64_t ti = ceil_div(I, BT);
+  if (ti > 0x7fffffffLL) return fail(GCS_ERR_INVALID_ARGUMENT, "%s: too many row tiles", who);
+  dim3 grid(static_cast<unsigned>(ti), static_cast<unsigned>(ceil_div(J, BT)), splits);
+  if (vec)
+    sgemm_kernel<P_RC, Q_JC, true><<<grid, kGemmThreads, 0, st>>>(P, ldp, Q, ldq, C, ldc, bias, I, J, R, r_per_split, accumulate, c_split_stride);
+  else
+    sgemm_kernel<P_RC, Q_JC, false><<<grid, kGemmThreads, 0, st>>>(P, ldp, Q, ldq, C, ldc, bias, I, J, R, r_per_split, accumulate, c_split_stride);
+  GCS_CHECK_LAUNCH(who);
+  return GCS_OK;
+}
+
+extern "C" int gcs_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C,
+                              int64_t ldc, int64_t M, int32_t K, int32_t N, gcs_stream stream) {
+  GCS_CHECK_ARG(M >= 0 && K > 0 && N > 0, "gcs_linear_fwd: bad size M=%lld K=%d N=%d", (long long)M, K, N);
+  if (M == 0) return GCS_OK;
+  GCS_CHECK_ARG(A && W && C && lda >= K && ldc >= N, "gcs_linear_fwd: bad pointer / leading dimension");
+  const bool vec = K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(W) &&
+                   aligned16(C) && (!bias || aligned16(bias));
+  return launch_sgemm<true, true>(A, lda, W, N, C, ldc, bias, M, N, K, 1, K, 0, 0, vec, as_stream(stream), "gcs_linear_fwd");
+}
+
+extern "C" int gcs_linear_bwd_input(const float* dH, int64_t ldh, const float* W, float* dA, int64_t lda,
+                                    int64_t M, int32_t K, int32_t N, int32_t accumulate, gcs_stream stream) {
+  GCS_CHECK_ARG(M >= 0 && K > 0 && N > 0, "gcs_linear_bwd_input: bad size");
+  if (M == 0) return GCS_OK;
+  GCS_CHECK_ARG(dH && W && dA && ldh >= N && lda >= K, "gcs_linear_bwd_input: bad pointer / leading dimension");
+  const bool vec = K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldh % 4 == 0 && aligned16(dH) && aligned16(W) && aligned16(dA);
+  // C[i=m, j=k] = sum_{r=n} dH[m, n] * W[k, n]
+  return launch_sgemm<true, false>(dH, ldh, W, N, dA, lda, nullptr, M, K, N, 1, N, accumulate, 0, vec, as_stream(stream), "gcs_linear_bwd_input");
+}
+
+extern "C" int64_t gcs_linear_bwd_weight_workspace_bytes(int64_t M, int32_t K, int32_t N) {
+  if (M < 0 || K <= 0 || N <= 0) return 0;
+  const WeightSplit w = weight_split(M, K, N);
+  return round_up(static_cast<int64_t>(w.splits) * K * N * sizeof(float), 256) +
+         round_up(static_cast<int64_t>(w.col_splits) * N * sizeof(double), 256);
+}
+
+extern "C" int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* dH, int64_t ldh, float* dW,
+                                     float* db, int64_t M, int32_t K, int32_t N, void* workspace,
+                                     int64_t workspace_bytes, gcs_stream stream) {
+  GCS_CHECK_ARG(M > 0 && K > 0 && N > 0, "gcs_linear_bwd_weight: bad size");
+  GCS_CHECK_ARG(A && dH && dW && workspace && lda >= K && ldh >= N, "gcs_linear_bwd_weight: bad pointer / leading dimension");
+  if (workspace_bytes < gcs_linear_bwd_weight_workspace_bytes(M, K, N))
+    return fail(GCS_ERR_WORKSPACE, "gcs_linear_bwd_weight: workspace %lld < %lld bytes", (long long)workspace_bytes,
+                (long long)gcs_linear_bwd_weight_workspace_bytes(M, K, N));
+  GCS_CHECK_ARG(aligned16(workspace), "gcs_linear_bwd_weight: workspace must be 16-byte aligned");
+  const WeightSplit w = weight_split(M, K, N);
+  cudaStream_t st = as_stream(stream);
+  float* part = static_cast<float*>(workspace);
+  const bool vec = K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldh % 4 == 0 && aligned16(A) && aligned16(dH) && aligned16(dW);
+  const int64_t kn = static_cast<int64_t>(K) * N;
+  // C[i=k, j=n] = sum_{r=m} A[m, k] * dH[m, n]
+  if (w.splits == 1) {
+    GCS_TRY((launch_sgemm<false, true>(A, lda, dH, ldh, dW, N, nullptr, K, N, M, 1, w.r_per_split, 0, 0, vec, st, "gcs_linear_bwd_weight")));
+  } else {
+    GCS_TRY((launch_sgemm<false, true>(A, lda, dH, ldh, part, N, nullptr, K, N, M, w.splits, w.r_per_split, 0, kn, vec, st, "gcs_linear_bwd_weight")));
+    int64_t blocks = ceil_div(kn, 256);
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    split_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(part, w.splits, kn, dW);
+    GCS_CHECK_LAUNCH("split_reduce_kernel");
+  }
+  if (db) {
+    double* cws = reinterpret_cast<double*>(static_cast<char*>(workspace) +
+                                            round_up(static_cast<int64_t>(w.splits) * kn * sizeof(float), 256));
+    dim3 grid(static_cast<unsigned>(ceil_div(N, 32)), w.col_splits);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(dH, ldh, M, N, w.col_rows_per_split, cws);
+    GCS_CHECK_LAUNCH("colsum_partial_kernel");
+    colsum_final_kernel<<<static_cast<unsigned>(ceil_div(N, 128)), 128, 0, st>>>(cws, w.col_splits, N, db);
+    GCS_CHECK_LAUNCH("colsum_final_kernel");
+  }
+  return GCS_OK;
+}

@@ -1,0 +1,435 @@
+// Whole-model entry points: spektral.models.GeneralGNN.__call__ and the reverse-mode
+// gradient the reference takes with tf.GradientTape (src/scripts/gcn.py:320 model,
+// :333-337 train step, :351 inference; upstream call graph in SURVEY.md §3.1, §8 a2).
+//
+//   out = pre(x)                                   MLP: [Dense -> BN -> PReLU] x P
+//   for k in 1..L:  z = A . prelu(bn(out.W_k + b_k));  out = concat([z, out])
+//   out = segment_sum(out, i);  out = post(out)    MLP, last layer Dense -> BN -> softmax
+//
+// HBM layout.  The 'cat' skip connection is materialised ONCE: a single [N, H*(L+1)] buffer
+// `cat`; Keras concatenates [z, out] (new block first), so pre() writes the LAST H columns
+// and layer k writes the H columns just before the current prefix — layer k's GEMM input
+// is the trailing k*H columns as a strided view (ld = H*(L+1)).  No ConcatV2 copies.  Per
+// dense block only the pre-BatchNorm output h is saved for the backward; BN+PReLU are
+// recomputed (fused into the aggregation's load in the conv blocks).  The backward keeps
+// one gradient buffer gcat of the same shape that the skip connections accumulate into.
+// The caller owns the workspace; nothing is allocated here.
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcs {
+
+struct BlockDesc {
+  int k_in, m_out;
+  bool has_alpha;
+  int64_t off;       // kernel offset in the trainable buffer
+  int64_t stat_off;  // moving_mean offset in the state buffer
+  int64_t kernel() const { return off; }
+  int64_t bias() const { return off + static_cast<int64_t>(k_in) * m_out; }
+  int64_t gamma() const { return bias() + m_out; }
+  int64_t beta() const { return gamma() + m_out; }
+  int64_t alpha() const { return beta() + m_out; }
+  int64_t count() const { return static_cast<int64_t>(k_in) * m_out + (has_alpha ? 4 : 3) * m_out; }
+};
+
+// Same arithmetic as gcn-string_b200/params.py:block_specs.
+static void build_blocks(const gcs_model_config& c, std::vector<BlockDesc>& out) {
+  out.clear();
+  int64_t off = 0, soff = 0;
+  auto push = [&](int k_in, int m_out, bool has_alpha) {
+    BlockDesc b{k_in, m_out, has_alpha, off, soff};
+    out.push_back(b);
+    off += b.count();
+    soff += 2 * m_out;
+  };
+  int k = c.in_features;
+  for (int j = 0; j < c.pre_process; ++j) { push(k, c.hidden, true); k = c.hidden; }
+  for (int j = 0; j < c.message_passing; ++j) push(c.hidden * (j + 1), c.hidden, true);
+  k = c.hidden * (c.message_passing + 1);
+  for (int j = 0; j < c.post_process; ++j) {
+    const bool last = j == c.post_process - 1;
+    push(k, last ? c.output : c.hidden, !last);
+    k = c.hidden;
+  }
+}
+
+static int check_config(const gcs_model_config* c) {
+  if (!c) return fail(GCS_ERR_INVALID_ARGUMENT, "model config is NULL");
+  if (c->in_features < 1 || c->output < 1 || c->hidden < 1)
+    return fail(GCS_ERR_INVALID_ARGUMENT, "model config: feature widths must be positive");
+  if (c->message_passing < 1 || c->pre_process < 1 || c->post_process < 1)
+    return fail(GCS_ERR_UNSUPPORTED, "model config: pre_process, message_passing, post_process must be >= 1");
+  if (c->connectivity != 1) return fail(GCS_ERR_UNSUPPORTED, "model config: only connectivity='cat' is built");
+  if (c->pool != 0 && c->pool != 1) return fail(GCS_ERR_UNSUPPORTED, "model config: pool must be 'sum' or None");
+  if (c->final_activation != 0 && c->final_activation != 1)
+    return fail(GCS_ERR_UNSUPPORTED, "model config: final activation must be linear or softmax");
+  if (c->final_activation == 1 && c->output > 64)
+    return fail(GCS_ERR_UNSUPPORTED, "model config: softmax over more than 64 classes is not built");
+  return GCS_OK;
+}
+
+// Bump allocator over the caller's workspace; with base == nullptr it only measures.
+struct Arena {
+  char* base;
+  int64_t used = 0;
+  explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(int64_t count) {
+    const int64_t bytes = round_up(count * static_cast<int64_t>(sizeof(T)), 256);
+    T* p = base ? reinterpret_cast<T*>(base + used) : nullptr;
+    used += bytes;
+    return p;
+  }
+};
+
+struct Plan {
+  std::vector<BlockDesc> blocks;
+  int P, L, Q, H, Wc, C;
+  int64_t N, rows_post;
+  int B;
+  // forward
+  float* cat = nullptr;
+  std::vector<float*> h;        // pre-BN outputs of the node-level blocks (P + L)
+  std::vector<float*> act;      // materialised activations of pre blocks 0..P-2
+  std::vector<float*> stat;     // per block: mean | var | scale | shift  (4 * m_out)
+  float* pooled = nullptr;      // [B, Wc] (unused when pool == 0)
+  std::vector<float*> post_h;   // [rows_post, m_out]
+  std::vector<float*> post_a;   // [rows_post, H], post blocks 0..Q-2
+  float* logits = nullptr;      // [rows_post, C]
+  void* bn_ws = nullptr;
+  int64_t bn_ws_bytes = 0;
+  // backward
+  float* gcat = nullptr;        // [N, Wc]
+  float* tmp_a = nullptr;       // [N, H]
+  float* tmp_b = nullptr;       // [N, H]
+  float* dlogits = nullptr;     // [rows_post, C]
+  float* dpost = nullptr;       // [rows_post, max(H, C)]  dh of a post block
+  float* dpost_in = nullptr;    // [rows_post, H]          gradient w.r.t. a post activation
+  float* dpooled = nullptr;     // [B, Wc]
+  void* lw_ws = nullptr;
+  int64_t lw_ws_bytes = 0;
+};
+
+static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training, void* ws, Plan& p, int64_t* total) {
+  build_blocks(c, p.blocks);
+  p.P = c.pre_process; p.L = c.message_passing; p.Q = c.post_process;
+  p.H = c.hidden; p.Wc = c.hidden * (c.message_passing + 1); p.C = c.output;
+  p.N = N; p.B = B;
+  p.rows_post = c.pool ? B : N;
+  Arena a(ws);
+  const int64_t NH = N * p.H;
+  p.cat = a.take<float>(N * p.Wc);
+  p.h.assign(p.P + p.L, nullptr);
+  if (training) {
+    for (auto& q : p.h) q = a.take<float>(NH);
+  } else {
+    float* shared = a.take<float>(NH);
+    for (auto& q : p.h) q = shared;
+  }
+  p.act.assign(p.P > 1 ? p.P - 1 : 0, nullptr);
+  if (training) {
+    for (auto& q : p.act) q = a.take<float>(NH);
+  } else if (p.P > 1) {
+    float* pp[2] = {a.take<float>(NH), p.P > 2 ? a.take<float>(NH) : nullptr};
+    for (size_t j = 0; j < p.act.size(); ++j) p.act[j] = pp[j & 1];
+  }
+  p.stat.clear();
+  for (const auto& b : p.blocks) p.stat.push_back(a.take<float>(4LL * b.m_out));
+  if (c.pool) p.pooled = a.take<float>(static_cast<int64_t>(B) * p.Wc);
+  p.post_h.clear(); p.post_a.clear();
+  for (int j = 0; j < p.Q; ++j) {
+    const auto& b = p.blocks[p.P + p.L + j];
+    p.post_h.push_back(a.take<float>(p.rows_post * b.m_out));
+    if (j < p.Q - 1) p.post_a.push_back(a.take<float>(p.rows_post * p.H));
+  }
+  p.logits = a.take<float>(p.rows_post * p.C);
+  int64_t bn_bytes = gcs_bn_workspace_bytes(N, p.H);
+  for (int j = 0; j < p.Q; ++j) {
+    const int64_t v = gcs_bn_workspace_bytes(p.rows_post, p.blocks[p.P + p.L + j].m_out);
+    if (v > bn_bytes) bn_bytes = v;
+  }
+  p.bn_ws_bytes = bn_bytes;
+  p.bn_ws = a.take<char>(bn_bytes);
+  if (training) {
+    p.gcat = a.take<float>(N * p.Wc);
+    p.tmp_a = a.take<float>(NH);
+    p.tmp_b = a.take<float>(NH);
+    p.dlogits = a.take<float>(p.rows_post * p.C);
+    p.dpost = a.take<float>(p.rows_post * (p.H > p.C ? p.H : p.C));
+    p.dpost_in = a.take<float>(p.rows_post * p.H);
+    if (c.pool) p.dpooled = a.take<float>(static_cast<int64_t>(B) * p.Wc);
+    int64_t lw = 0;
+    for (size_t i = 0; i < p.blocks.size(); ++i) {
+      const int64_t rows = static_cast<int>(i) < p.P + p.L ? N : p.rows_post;
+      const int64_t v = gcs_linear_bwd_weight_workspace_bytes(rows, p.blocks[i].k_in, p.blocks[i].m_out);
+      if (v > lw) lw = v;
+    }
+    p.lw_ws_bytes = lw;
+    p.lw_ws = a.take<char>(lw);
+  }
+  *total = a.used;
+}
+
+static int check_batch(const gcs_model_config& c, const gcs_batch* b, bool need_labels, bool need_transpose) {
+  if (!b) return fail(GCS_ERR_INVALID_ARGUMENT, "batch is NULL");
+  if (b->n_nodes <= 0) return fail(GCS_ERR_INVALID_ARGUMENT, "batch has no nodes");
+  if (b->nnz < 0) return fail(GCS_ERR_INVALID_ARGUMENT, "batch has negative nnz");
+  if (!b->rowptr || (b->nnz > 0 && !b->colidx) || !b->x)
+    return fail(GCS_ERR_INVALID_ARGUMENT, "batch: rowptr / colidx / x must be set");
+  if (b->ldx < c.in_features) return fail(GCS_ERR_INVALID_ARGUMENT, "batch: ldx < in_features");
+  if (c.pool && (b->n_graphs <= 0 || !b->graph_ptr))
+    return fail(GCS_ERR_INVALID_ARGUMENT, "batch: pooling needs n_graphs > 0 and graph_ptr (the batch index i)");
+  if (need_labels && !b->y) return fail(GCS_ERR_INVALID_ARGUMENT, "batch: training needs labels y");
+  if (need_transpose && (!b->rowptr_t || (b->nnz > 0 && !b->colidx_t)))
+    return fail(GCS_ERR_INVALID_ARGUMENT, "batch: the backward needs the transposed CSR (alias it if symmetric)");
+  return GCS_OK;
+}
+
+// BatchNorm statistics -> folded scale/shift for block bi over `rows` rows of h.
+static int block_norm(const gcs_model_config& c, const Plan& p, int bi, const float* params, float* state,
+                      const float* h, int64_t ldh, int64_t rows, bool training, gcs_stream st) {
+  const BlockDesc& b = p.blocks[bi];
+  float* mean = p.stat[bi];
+  float* var = mean + b.m_out;
+  float* scale = var + b.m_out;
+  float* shift = scale + b.m_out;
+  float* mm = state + b.stat_off;
+  float* mv = mm + b.m_out;
+  if (training) {
+    GCS_TRY(gcs_bn_stats(h, ldh, rows, b.m_out, mean, var, p.bn_ws, p.bn_ws_bytes, st));
+    GCS_TRY(gcs_bn_fold(mean, var, params + b.gamma(), params + b.beta(), c.bn_epsilon, c.bn_momentum, mm, mv,
+                        scale, shift, b.m_out, st));
+  } else {
+    GCS_TRY(gcs_bn_fold(mm, mv, params + b.gamma(), params + b.beta(), c.bn_epsilon, c.bn_momentum, nullptr,
+                        nullptr, scale, shift, b.m_out, st));
+  }
+  return GCS_OK;
+}
+
+// Everything up to the logits ([rows_post, C] in p.logits).
+static int run_forward(const gcs_model_config& c, const Plan& p, const float* params, float* state,
+                       const gcs_batch& bt, bool training, gcs_stream st) {
+  const int H = p.H, Wc = p.Wc, L = p.L, P = p.P;
+  const int64_t N = p.N;
+  // pre-processing MLP
+  const float* in = bt.x;
+  int64_t ld_in = bt.ldx;
+  for (int j = 0; j < P; ++j) {
+    const BlockDesc& b = p.blocks[j];
+    GCS_TRY(gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, st));
+    GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
+    float* out = j < P - 1 ? p.act[j] : p.cat + static_cast<int64_t>(L) * H;
+    const int64_t ld_out = j < P - 1 ? H : Wc;
+    const float* scale = p.stat[j] + 2 * H;
+    GCS_TRY(gcs_bn_prelu_fwd(p.h[j], H, scale, scale + H, params + b.alpha(), out, ld_out, N, H, st));
+    in = out;
+    ld_in = ld_out;
+  }
+  // message passing with in-place concat
+  for (int k = 0; k < L; ++k) {
+    const int bi = P + k;
+    const BlockDesc& b = p.blocks[bi];
+    const float* cin = p.cat + static_cast<int64_t>(L - k) * H;          // trailing (k+1)*H columns
+    GCS_TRY(gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, st));
+    GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
+    const float* scale = p.stat[bi] + 2 * H;
+    GCS_TRY(gcs_spmm_sum(bt.rowptr, bt.colidx, bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, N, p.h[bi], H,
+                         scale, scale + H, params + b.alpha(), p.cat + static_cast<int64_t>(L - k - 1) * H, Wc,
+                         H, st));
+  }
+  // global sum pool
+  const float* pin = p.cat;
+  int64_t ld_pin = Wc;
+  if (c.pool) {
+    GCS_TRY(gcs_segment_sum_fwd(p.cat, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.pooled, Wc, st));
+    pin = p.pooled;
+  }
+  // post-processing MLP
+  const int64_t R = p.rows_post;
+  for (int j = 0; j < p.Q; ++j) {
+    const int bi = P + L + j;
+    const BlockDesc& b = p.blocks[bi];
+    GCS_TRY(gcs_linear_fwd(pin, ld_pin, params + b.kernel(), params + b.bias(), p.post_h[j], b.m_out, R, b.k_in,
+                           b.m_out, st));
+    GCS_TRY(block_norm(c, p, bi, params, state, p.post_h[j], b.m_out, R, training, st));
+    const float* scale = p.stat[bi] + 2 * b.m_out;
+    if (j < p.Q - 1) {
+      GCS_TRY(gcs_bn_prelu_fwd(p.post_h[j], b.m_out, scale, scale + b.m_out, params + b.alpha(), p.post_a[j], H, R,
+                               b.m_out, st));
+      pin = p.post_a[j];
+      ld_pin = H;
+    } else {
+      GCS_TRY(gcs_bn_prelu_fwd(p.post_h[j], b.m_out, scale, scale + b.m_out, nullptr, p.logits, p.C, R, p.C, st));
+    }
+  }
+  return GCS_OK;
+}
+
+// Backward of one dense block given da = dLoss/d(block output): parameter gradients into
+// `grads`, dh left in `dh`; optionally the input gradient.
+static int block_backward(const gcs_model_config& c, const Plan& p, int bi, const float* params, float* grads,
+                          const float* da, int64_t ldda, const float* h, int64_t ldh, int64_t rows,
+                          const float* in, int64_t ld_in, float* dh, int64_t lddh, float* din, int64_t lddin,
+                          int accumulate, gcs_stream st) {
+  const BlockDesc& b = p.blocks[bi];
+  const float* mean = p.stat[bi];
+  const float* var = mean + b.m_out;
+  GCS_TRY(gcs_bn_prelu_bwd(da, ldda, h, ldh, mean, var, params + b.gamma(), params + b.beta(),
+                           b.has_alpha ? params + b.alpha() : nullptr, c.bn_epsilon, dh, lddh, grads + b.gamma(),
+                           grads + b.beta(), b.has_alpha ? grads + b.alpha() : nullptr, rows, b.m_out, p.bn_ws,
+                           p.bn_ws_bytes, st));
+  GCS_TRY(gcs_linear_bwd_weight(in, ld_in, dh, lddh, grads + b.kernel(), grads + b.bias(), rows, b.k_in, b.m_out,
+                                p.lw_ws, p.lw_ws_bytes, st));
+  if (din)
+    GCS_TRY(gcs_linear_bwd_input(dh, lddh, params + b.kernel(), din, lddin, rows, b.k_in, b.m_out, accumulate, st));
+  return GCS_OK;
+}
+
+// Reverse pass given dlogits = dLoss/d(logits) [rows_post, C]; needs the activations a
+// training-mode run_forward left in the workspace.
+static int run_backward(const gcs_model_config& c, const Plan& p, const float* params, float* grads,
+                        const gcs_batch& bt, const float* dlogits, gcs_stream st) {
+  const int H = p.H, Wc = p.Wc, L = p.L, P = p.P, Q = p.Q;
+  const int64_t N = p.N, R = p.rows_post;
+  // ---- post-processing MLP, last block first
+  const float* da = dlogits;
+  int64_t ldda = p.C;
+  for (int j = Q - 1; j >= 0; --j) {
+    const int bi = P + L + j;
+    const BlockDesc& b = p.blocks[bi];
+    const float* in = j == 0 ? (c.pool ? p.pooled : p.cat) : p.post_a[j - 1];
+    const int64_t ld_in = j == 0 ? Wc : H;
+    float* din;
+    int64_t lddin;
+    if (j == 0) { din = c.pool ? p.dpooled : p.gcat; lddin = Wc; }
+    else { din = p.dpost_in; lddin = H; }
+    GCS_TRY(block_backward(c, p, bi, params, grads, da, ldda, p.post_h[j], b.m_out, R, in, ld_in, p.dpost, b.m_out,
+                           din, lddin, 0, st));
+    da = din;
+    ldda = lddin;
+  }
+  // ---- pool: dX[n] = dOut[i[n]]
+  if (c.pool) GCS_TRY(gcs_segment_sum_bwd(p.dpooled, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.gcat, Wc, st));
+  // ---- message passing, last layer first; skip gradients accumulate into gcat in place
+  for (int k = L - 1; k >= 0; --k) {
+    const int bi = P + k;
+    const float* dz = p.gcat + static_cast<int64_t>(L - k - 1) * H;
+    GCS_TRY(gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, N, dz, Wc,
+                         nullptr, nullptr, nullptr, p.tmp_a, H, H, st));
+    GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N,
+                           p.cat + static_cast<int64_t>(L - k) * H, Wc, p.tmp_b, H,
+                           p.gcat + static_cast<int64_t>(L - k) * H, Wc, 1, st));
+  }
+  // ---- pre-processing MLP
+  da = p.gcat + static_cast<int64_t>(L) * H;
+  ldda = Wc;
+  for (int j = P - 1; j >= 0; --j) {
+    const float* in = j == 0 ? bt.x : p.act[j - 1];
+    const int64_t ld_in = j == 0 ? bt.ldx : H;
+    GCS_TRY(block_backward(c, p, j, params, grads, da, ldda, p.h[j], H, N, in, ld_in, p.tmp_b, H,
+                           j > 0 ? p.tmp_a : nullptr, H, 0, st));
+    da = p.tmp_a;
+    ldda = H;
+  }
+  return GCS_OK;
+}
+
+}  // namespace gcs
+
+using namespace gcs;
+
+extern "C" int64_t gcs_model_num_params(const gcs_model_config* cfg) {
+  if (check_config(cfg) != GCS_OK) return -1;
+  std::vector<BlockDesc> blocks;
+  build_blocks(*cfg, blocks);
+  return blocks.back().off + blocks.back().count();
+}
+
+extern "C" int64_t gcs_model_num_state(const gcs_model_config* cfg) {
+  if (check_config(cfg) != GCS_OK) return -1;
+  std::vector<BlockDesc> blocks;
+  build_blocks(*cfg, blocks);
+  return blocks.back().stat_off + 2LL * blocks.back().m_out;
+}
+
+extern "C" int64_t gcs_model_workspace_bytes(const gcs_model_config* cfg, int64_t n_nodes, int64_t nnz,
+                                             int32_t n_graphs, int32_t training) {
+  (void)nnz;
+  if (check_config(cfg) != GCS_OK || n_nodes < 0 || n_graphs < 0) return -1;
+  Plan p;
+  int64_t total = 0;
+  make_plan(*cfg, n_nodes, n_graphs, training != 0, nullptr, p, &total);
+  return total;
+}
+
+extern "C" int gcs_model_forward(const gcs_model_config* cfg, const float* params, float* state,
+                                 const gcs_batch* batch, int32_t training, float* out, void* workspace,
+                                 int64_t workspace_bytes, gcs_stream stream) {
+  GCS_TRY(check_config(cfg));
+  GCS_TRY(check_batch(*cfg, batch, false, false));
+  GCS_CHECK_ARG(params && state && out && workspace, "gcs_model_forward: null pointer");
+  GCS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "gcs_model_forward: workspace must be 256-byte aligned");
+  Plan p;
+  int64_t total = 0;
+  make_plan(*cfg, batch->n_nodes, batch->n_graphs, training != 0, workspace, p, &total);
+  if (workspace_bytes < total)
+    return fail(GCS_ERR_WORKSPACE, "gcs_model_forward: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
+  GCS_TRY(run_forward(*cfg, p, params, state, *batch, training != 0, stream));
+  if (cfg->final_activation == 1) {
+    GCS_CHECK_ARG(p.rows_post < INT32_MAX, "gcs_model_forward: too many output rows");
+    GCS_TRY(gcs_softmax_xent(p.logits, nullptr, static_cast<int32_t>(p.rows_post), p.C, out, nullptr, nullptr, 0.f, stream));
+  } else {
+    GCS_CUDA(cudaMemcpyAsync(out, p.logits, sizeof(float) * p.rows_post * p.C, cudaMemcpyDeviceToDevice, as_stream(stream)));
+  }
+  return GCS_OK;
+}
+
+extern "C" int gcs_model_train_step(const gcs_model_config* cfg, const float* params, float* state,
+                                    const gcs_batch* batch, float grad_scale, float* grads, float* probs,
+                                    float* loss_acc, void* workspace, int64_t workspace_bytes,
+                                    gcs_stream stream) {
+  GCS_TRY(check_config(cfg));
+  GCS_TRY(check_batch(*cfg, batch, true, true));
+  GCS_CHECK_ARG(cfg->final_activation == 1, "gcs_model_train_step: the loss is categorical cross-entropy on a softmax output");
+  GCS_CHECK_ARG(params && state && grads && loss_acc && workspace, "gcs_model_train_step: null pointer");
+  GCS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "gcs_model_train_step: workspace must be 256-byte aligned");
+  const gcs_model_config& c = *cfg;
+  const gcs_batch& bt = *batch;
+  Plan p;
+  int64_t total = 0;
+  make_plan(c, bt.n_nodes, bt.n_graphs, true, workspace, p, &total);
+  if (workspace_bytes < total)
+    return fail(GCS_ERR_WORKSPACE, "gcs_model_train_step: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
+  GCS_CHECK_ARG(p.rows_post < INT32_MAX, "gcs_model_train_step: too many output rows");
+  GCS_TRY(run_forward(c, p, params, state, bt, true, stream));
+  GCS_TRY(gcs_softmax_xent(p.logits, bt.y, static_cast<int32_t>(p.rows_post), p.C, probs, loss_acc, p.dlogits,
+                           grad_scale, stream));
+
+  return run_backward(c, p, params, grads, bt, p.dlogits, stream);
+}
+
+extern "C" int64_t gcs_model_logits_offset(const gcs_model_config* cfg, int64_t n_nodes, int32_t n_graphs,
+                                           int32_t training) {
+  if (check_config(cfg) != GCS_OK || n_nodes < 0 || n_graphs < 0) return -1;
+  Plan p;
+  int64_t total = 0;
+  // measure against a fake non-null base so that pointers are offsets + 256
+  make_plan(*cfg, n_nodes, n_graphs, training != 0, reinterpret_cast<void*>(256), p, &total);
+  return reinterpret_cast<char*>(p.logits) - reinterpret_cast<char*>(256);
+}
+
+extern "C" int gcs_model_backward(const gcs_model_config* cfg, const float* params, const gcs_batch* batch,
+                                  const float* dlogits, float* grads, void* workspace, int64_t workspace_bytes,
+                                  gcs_stream stream) {
+  GCS_TRY(check_config(cfg));
+  GCS_TRY(check_batch(*cfg, batch, false, true));
+  GCS_CHECK_ARG(params && dlogits && grads && workspace, "gcs_model_backward: null pointer");
+  GCS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "gcs_model_backward: workspace must be 256-byte aligned");
+  Plan p;
+  int64_t total = 0;
+  make_plan(*cfg, batch->n_nodes, batch->n_graphs, true, workspace, p, &total);
+  if (workspace_bytes < total)
+    return fail(GCS_ERR_WORKSPACE, "gcs_model_backward: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
+  return run_backward(*cfg, p, params, grads, *batch, dlogits, stream);
+}

@@ -1,0 +1,313 @@
+"""Data side of the drop-in surface: ``Graph``, ``Dataset``, ``DisjointLoader``.
+
+Mirrors the parts of ``spektral.data`` the reference uses (src/scripts/gcn.py:9 import,
+:66-197 ``MyDataset(Dataset)``, :293-294 ``dataset[idx_array]``, :316-317 loaders, :328
+``tf_signature()``, :348,372 ``steps_per_epoch``, :350,367 iteration).  Upstream's collate
+(np.vstack / sp.block_diag / sp.find / tf.sparse.reorder / np.repeat on the host, every
+step) is replaced by ONE upload of the packed dataset into HBM and a
+device batching kernel per step (csrc/batching.cu); the host only slices the epoch
+permutation and sums per-graph sizes.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
+from .synthetic import PackedGraphs, pack_graphs
+
+
+class Graph:
+    """``spektral.data.Graph``: container for x [n,F], a [n,n] (scipy sparse / ndarray), e, y."""
+
+    def __init__(self, x=None, a=None, e=None, y=None, **kwargs):
+        self.x, self.a, self.e, self.y = x, a, e, y
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def n_nodes(self):
+        return self.x.shape[0] if self.x is not None else self.a.shape[0]
+
+    @property
+    def n_node_features(self):
+        return self.x.shape[-1] if self.x is not None else None
+
+    @property
+    def n_labels(self):
+        if self.y is None:
+            return None
+        shp = np.shape(self.y)
+        return 1 if len(shp) == 0 else shp[-1]
+
+    def numpy(self):
+        return tuple(v for v in (self.x, self.a, self.e, self.y) if v is not None)
+
+    def __repr__(self):
+        return f"Graph(n_nodes={self.n_nodes}, n_node_features={self.n_node_features}, n_labels={self.n_labels})"
+
+
+class Dataset:
+    """``spektral.data.Dataset``: subclass and implement ``read()`` returning a list of Graph
+    (the reference's MyDataset, gcn.py:66-102).  Supports ``len``, iteration, and indexing by
+    int / slice / integer or boolean array (gcn.py:293-294)."""
+
+    def __init__(self, transforms=None, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+        self.graphs = self.read()
+        if len(self.graphs) == 0:
+            raise ValueError("Datasets cannot be empty")
+        if transforms is not None:
+            for t in (transforms if isinstance(transforms, (list, tuple)) else [transforms]):
+                self.graphs = [t(g) for g in self.graphs]
+
+    def read(self) -> List[Graph]:
+        raise NotImplementedError
+
+    @classmethod
+    def from_graphs(cls, graphs: Sequence[Graph]) -> "Dataset":
+        ds = cls.__new__(cls)
+        ds.graphs = list(graphs)
+        return ds
+
+    def __len__(self):
+        return len(self.graphs)
+
+    def __iter__(self):
+        return iter(self.graphs)
+
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)):
+            return self.graphs[int(key)]
+        if isinstance(key, slice):
+            return Dataset.from_graphs(self.graphs[key])
+        key = np.asarray(key)
+        if key.dtype == bool:
+            key = np.nonzero(key)[0]
+        return Dataset.from_graphs([self.graphs[int(k)] for k in key])
+
+    def __setitem__(self, key, value):
+        self.graphs[key] = value
+
+    @property
+    def n_graphs(self):
+        return len(self)
+
+    @property
+    def n_node_features(self):
+        return self.graphs[0].n_node_features
+
+    @property
+    def n_labels(self):
+        return self.graphs[0].n_labels
+
+
+class SparseAdjacency:
+    """What the loader yields as ``a``: a SparseTensor-like view (``indices`` [nnz,2] int64
+    row-major, ``values``, ``dense_shape``) over a device CSR.  The CSR (+ its transpose,
+    aliased when the pattern is symmetric) is what the kernels consume; ``indices`` is only
+    materialised on request.  ``values`` exist for API compatibility and are never read:
+    GeneralConv ignores adjacency values."""
+
+    def __init__(self, rowptr, colidx, n_rows, graph_ptr=None, max_graph_nodes=0, indices=None,
+                 symmetric: Optional[bool] = None):
+        self.rowptr, self.colidx = rowptr, colidx
+        self.n_rows = int(n_rows)
+        self.graph_ptr = graph_ptr
+        self.max_graph_nodes = int(max_graph_nodes)
+        self._indices = indices
+        self._symmetric = symmetric
+        self._t = None
+
+    @classmethod
+    def from_indices(cls, indices, dense_shape, values=None):
+        """From a canonical (row-major sorted) SparseTensor triple."""
+        n = int(dense_shape[0])
+        if int(dense_shape[1]) != n:
+            raise ValueError("A must be square")
+        torch = _lib.require_cuda()
+        idx = _lib.as_tensor(indices)
+        if not idx.is_cuda:
+            idx = idx.cuda()
+        rowptr, colidx = ops.coo_to_csr(idx.to(torch.int64), n)
+        return cls(rowptr, colidx, n, indices=idx)
+
+    @property
+    def nnz(self):
+        return int(self.colidx.shape[0])
+
+    @property
+    def dense_shape(self):
+        return (self.n_rows, self.n_rows)
+
+    shape = dense_shape
+
+    @property
+    def indices(self):
+        if self._indices is None:
+            torch = _lib.require_cuda()
+            counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            rows = torch.repeat_interleave(torch.arange(self.n_rows, device="cuda"), counts)
+            self._indices = torch.stack([rows, self.colidx.to(torch.int64)], dim=1)
+        return self._indices
+
+    @property
+    def values(self):
+        torch = _lib.require_cuda()
+        return torch.ones(self.nnz, dtype=torch.int64, device="cuda")
+
+    @property
+    def symmetric(self) -> bool:
+        if self._symmetric is None:
+            self._symmetric = ops.csr_is_symmetric(self.rowptr, self.colidx)
+        return self._symmetric
+
+    def transposed(self):
+        """(rowptr_t, colidx_t) of pattern(A)^T; the same arrays when symmetric."""
+        if self._t is None:
+            self._t = (self.rowptr, self.colidx) if self.symmetric else ops.csr_transpose(self.rowptr, self.colidx)
+        return self._t
+
+
+class DeviceGraphStore:
+    """The packed dataset resident in HBM + the host-side per-graph sizes."""
+
+    def __init__(self, packed: PackedGraphs, symmetric: Optional[bool] = None):
+        torch = _lib.require_cuda()
+        _lib.load()
+        self.n_graphs = packed.n_graphs
+        self.n_feat = int(packed.x.shape[1])
+        self.n_classes = int(packed.y.shape[1]) if packed.y.ndim == 2 else 0
+        self.h_n_nodes = packed.n_nodes.astype(np.int64)
+        self.h_n_edges = packed.n_edges.astype(np.int64)
+        self.node_off = torch.from_numpy(packed.node_off).cuda()
+        self.rowptr = torch.from_numpy(packed.rowptr).cuda()
+        self.col = torch.from_numpy(packed.col).cuda()
+        self.x = torch.from_numpy(np.ascontiguousarray(packed.x, dtype=np.float32)).cuda()
+        self.y = torch.from_numpy(np.ascontiguousarray(packed.y, dtype=np.float32)).cuda() if self.n_classes else None
+        self.symmetric = symmetric
+
+    def batch(self, graph_ids_dev, graph_ids_host, want_coo=False, want_labels=True):
+        """Run K0 for the graphs ``graph_ids`` (device int64 tensor + the same ids on host)."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        b = int(graph_ids_host.shape[0])
+        n = int(self.h_n_nodes[graph_ids_host].sum())
+        nnz = int(self.h_n_edges[graph_ids_host].sum())
+        max_nodes = int(self.h_n_nodes[graph_ids_host].max()) if b else 0
+        i32 = dict(dtype=torch.int32, device="cuda")
+        graph_ptr = torch.empty(b + 1, **i32)
+        edge_ptr = torch.empty(b + 1, **i32)
+        rowptr = torch.empty(n + 1, **i32)
+        colidx = torch.empty(nnz, **i32)
+        x = torch.empty(n, self.n_feat, dtype=torch.float32, device="cuda")
+        seg = torch.empty(n, dtype=torch.int64, device="cuda")
+        y = torch.empty(b, self.n_classes, dtype=torch.float32, device="cuda") if (want_labels and self.y is not None) else None
+        coo = torch.empty(nnz, 2, dtype=torch.int64, device="cuda") if want_coo else None
+        flag = torch.zeros(1, **i32)
+        check(lib.gcs_batch_disjoint(ptr(self.node_off), ptr(self.rowptr), ptr(self.col), ptr(self.x), ptr(self.y),
+                                     self.n_feat, max(self.n_classes, 1), ptr(graph_ids_dev), b, n, nnz,
+                                     ptr(graph_ptr), ptr(edge_ptr), ptr(rowptr), ptr(colidx), ptr(x), ptr(seg),
+                                     ptr(y), ptr(coo), ptr(flag), stream_ptr()), "gcs_batch_disjoint")
+        a = SparseAdjacency(rowptr, colidx, n, graph_ptr=graph_ptr, max_graph_nodes=max_nodes, indices=coo,
+                            symmetric=self.symmetric)
+        a.edge_ptr = edge_ptr
+        a.status = flag
+        return x, a, seg, y
+
+
+class _Spec:
+    """Stand-in for tf.TensorSpec / tf.SparseTensorSpec in ``tf_signature()``."""
+
+    def __init__(self, shape, dtype, sparse=False):
+        self.shape, self.dtype, self.sparse = shape, dtype, sparse
+
+    def __repr__(self):
+        return f"{'Sparse' if self.sparse else ''}TensorSpec(shape={self.shape}, dtype={self.dtype})"
+
+
+class DisjointLoader:
+    """``spektral.data.DisjointLoader(dataset, node_level=False, batch_size=1, epochs=None,
+    shuffle=True)``.  Iterating yields ``((x, a, i), y)`` with everything on the device.
+
+    Batch order follows upstream's ``batch_generator``: per epoch an in-place
+    ``np.random.shuffle`` (cumulative across epochs, global NumPy RNG), then consecutive
+    slices of ``batch_size``; the last batch may be short; ``steps_per_epoch =
+    ceil(len / batch_size)``.  ``dataset`` may be a ``Dataset``, a list of ``Graph`` or an
+    already packed ``PackedGraphs``.  ``rank`` / ``world_size`` shard every global batch by
+    graph across data-parallel ranks (rank r takes the r-th contiguous part of the slice).
+    """
+
+    def __init__(self, dataset, node_level=False, batch_size=1, epochs=None, shuffle=True, rank=0, world_size=1,
+                 want_coo=False, symmetric=None):
+        if node_level:
+            raise NotImplementedError("node_level=True labels are not built (reference uses graph labels)")
+        packed = dataset if isinstance(dataset, PackedGraphs) else pack_graphs(list(dataset))
+        if packed.n_graphs == 0:
+            raise ValueError("Datasets cannot be empty")
+        self.dataset = dataset
+        self.store = DeviceGraphStore(packed, symmetric=symmetric)
+        self.node_level = node_level
+        self.batch_size = int(batch_size)
+        self.epochs = epochs
+        self.shuffle = shuffle
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.want_coo = want_coo
+        self._n = packed.n_graphs
+        self._order = np.arange(self._n, dtype=np.int64)
+        self._order_dev = None
+        self._generator = self._generate()
+
+    @property
+    def steps_per_epoch(self) -> int:
+        return int(np.ceil(self._n / self.batch_size))
+
+    def __len__(self):
+        return self.steps_per_epoch
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return next(self._generator)
+
+    def load(self):
+        return self
+
+    def tf_signature(self):
+        """Shape/dtype contract of one batch (gcn.py:328): dynamic N, nnz, B."""
+        f, c = self.store.n_feat, self.store.n_classes
+        return ((_Spec((None, f), "float32"), _Spec((None, None), "int64", sparse=True), _Spec((None,), "int64")),
+                _Spec((None, c), "float32"))
+
+    def _slices(self, start, stop):
+        """This rank's contiguous part of the global slice [start, stop)."""
+        if self.world_size == 1:
+            return start, stop
+        n = stop - start
+        base, rem = divmod(n, self.world_size)
+        lo = start + self.rank * base + min(self.rank, rem)
+        return lo, lo + base + (1 if self.rank < rem else 0)
+
+    def _generate(self):
+        torch = _lib.require_cuda()
+        epochs = np.inf if self.epochs is None or self.epochs == -1 else self.epochs
+        epoch = 0
+        while epoch < epochs:
+            epoch += 1
+            if self.shuffle:
+                np.random.shuffle(self._order)
+            if self.shuffle or self._order_dev is None:
+                self._order_dev = torch.from_numpy(self._order).cuda()
+            for b in range(self.steps_per_epoch):
+                start = b * self.batch_size
+                stop = min(start + self.batch_size, self._n)
+                lo, hi = self._slices(start, stop)
+                if hi <= lo:
+                    raise RuntimeError("a data-parallel rank received an empty shard; use batch_size >= world_size")
+                x, a, i, y = self.store.batch(self._order_dev[lo:hi], self._order[lo:hi], want_coo=self.want_coo)
+                a.global_batch_graphs = stop - start
+                yield (x, a, i), y

@@ -1,0 +1,313 @@
+"""Thin functional wrappers: one Python function per C-ABI entry point.
+
+They take torch CUDA tensors (or DLPack objects), validate dtype / device / row-major
+layout, allocate the outputs and workspaces with torch's caching allocator, and enqueue on
+torch's current stream.  No arithmetic happens in Python.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+from . import _lib
+from ._lib import as_tensor, check, ptr, stream_ptr
+
+
+def _t():
+    return _lib.require_cuda()
+
+
+def _mat(t, name, dtype=None):
+    """Validate a row-major 2-D view; returns (tensor, leading dimension)."""
+    torch = _t()
+    t = as_tensor(t)
+    dtype = dtype or torch.float32
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be rank 2, got shape {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError(f"{name} must be row-major (unit stride along the last axis)")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    if ld < t.shape[1]:
+        raise ValueError(f"{name}: overlapping rows are not supported")
+    return t, ld
+
+
+def _vec(t, name, dtype=None, n=None):
+    torch = _t()
+    t = as_tensor(t)
+    dtype = dtype or torch.float32
+    if not t.is_cuda or t.dtype != dtype or t.dim() != 1 or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous 1-D CUDA {dtype} tensor")
+    if n is not None and t.shape[0] != n:
+        raise ValueError(f"{name} must have {n} elements, got {t.shape[0]}")
+    return t
+
+
+def _ws(nbytes):
+    torch = _t()
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda")
+
+
+def check_status_flag(flag, what):
+    """Host read of a device status word (synchronises)."""
+    if int(flag.item()) != 0:
+        raise ValueError(what)
+
+
+# ------------------------------------------------------------------ structure (K0)
+def coo_to_csr(indices, n_rows: int, validate: bool = True):
+    """Row-major sorted int64 COO [nnz, 2] -> (rowptr int32 [n_rows+1], colidx int32 [nnz])."""
+    torch = _t()
+    lib = _lib.load()
+    indices = as_tensor(indices)
+    if indices.dtype != torch.int64 or indices.dim() != 2 or indices.shape[1] != 2:
+        raise ValueError("A.indices must be int64 of shape [nnz, 2] (a rank-2 SparseTensor)")
+    indices = indices.contiguous()
+    nnz = indices.shape[0]
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device="cuda")
+    colidx = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.gcs_coo_to_csr(ptr(indices), nnz, n_rows, ptr(rowptr), ptr(colidx), ptr(flag), stream_ptr()),
+          "gcs_coo_to_csr")
+    if validate:
+        check_status_flag(flag, "A.indices must be in canonical row-major order with in-range entries "
+                                "(tf.sparse.reorder); got unsorted, duplicate or out-of-range indices")
+    return rowptr, colidx
+
+
+def segment_ptr(seg_ids, n_graphs: int, validate: bool = True):
+    torch = _t()
+    lib = _lib.load()
+    seg_ids = _vec(seg_ids, "i", torch.int64)
+    gp = torch.empty(n_graphs + 1, dtype=torch.int32, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.gcs_segment_ptr(ptr(seg_ids), seg_ids.shape[0], n_graphs, ptr(gp), ptr(flag), stream_ptr()),
+          "gcs_segment_ptr")
+    if validate:
+        check_status_flag(flag, "the batch index i must be sorted and within [0, n_graphs)")
+    return gp
+
+
+def csr_is_symmetric(rowptr, colidx) -> bool:
+    torch = _t()
+    lib = _lib.load()
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.gcs_csr_is_symmetric(ptr(rowptr), ptr(colidx), rowptr.shape[0] - 1, ptr(flag), stream_ptr()),
+          "gcs_csr_is_symmetric")
+    return bool(flag.item())
+
+
+def csr_transpose(rowptr, colidx):
+    torch = _t()
+    lib = _lib.load()
+    n = rowptr.shape[0] - 1
+    nnz = colidx.shape[0]
+    rp_t = torch.empty_like(rowptr)
+    ci_t = torch.empty_like(colidx)
+    ws = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    check(lib.gcs_csr_transpose(ptr(rowptr), ptr(colidx), n, nnz, ptr(rp_t), ptr(ci_t), ptr(ws), stream_ptr()),
+          "gcs_csr_transpose")
+    return rp_t, ci_t
+
+
+def cast_f64_f32(x):
+    torch = _t()
+    lib = _lib.load()
+    x = as_tensor(x).contiguous()
+    out = torch.empty(x.shape, dtype=torch.float32, device="cuda")
+    check(lib.gcs_cast_f64_f32(ptr(x), ptr(out), x.numel(), stream_ptr()), "gcs_cast_f64_f32")
+    return out
+
+
+# ------------------------------------------------------------------ dense (K1/K9)
+def linear_fwd(a, w, bias=None, out=None):
+    torch = _t()
+    lib = _lib.load()
+    a, lda = _mat(a, "A")
+    w, ldw = _mat(w, "W")
+    if ldw != w.shape[1]:
+        raise ValueError("W must be contiguous")
+    m, k = a.shape
+    if w.shape[0] != k:
+        raise ValueError(f"shape mismatch: A is [{m},{k}], W is {tuple(w.shape)}")
+    n = w.shape[1]
+    if bias is not None:
+        bias = _vec(bias, "bias", n=n)
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device="cuda")
+    out, ldc = _mat(out, "C")
+    check(lib.gcs_linear_fwd(ptr(a), lda, ptr(w), ptr(bias), ptr(out), ldc, m, k, n, stream_ptr()), "gcs_linear_fwd")
+    return out
+
+
+def linear_bwd_weight(a, dh, want_db=True):
+    torch = _t()
+    lib = _lib.load()
+    a, lda = _mat(a, "A")
+    dh, ldh = _mat(dh, "dH")
+    m, k = a.shape
+    n = dh.shape[1]
+    if dh.shape[0] != m:
+        raise ValueError("A and dH must have the same number of rows")
+    dw = torch.empty(k, n, dtype=torch.float32, device="cuda")
+    db = torch.empty(n, dtype=torch.float32, device="cuda") if want_db else None
+    nb = lib.gcs_linear_bwd_weight_workspace_bytes(m, k, n)
+    ws = _ws(nb)
+    check(lib.gcs_linear_bwd_weight(ptr(a), lda, ptr(dh), ldh, ptr(dw), ptr(db), m, k, n, ptr(ws), ws.numel(),
+                                    stream_ptr()), "gcs_linear_bwd_weight")
+    return dw, db
+
+
+def linear_bwd_input(dh, w, out=None, accumulate=False):
+    torch = _t()
+    lib = _lib.load()
+    dh, ldh = _mat(dh, "dH")
+    w, _ = _mat(w, "W")
+    w = w.contiguous()
+    m, n = dh.shape
+    k = w.shape[0]
+    if w.shape[1] != n:
+        raise ValueError("dH and W disagree on the output width")
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs an existing output")
+        out = torch.empty(m, k, dtype=torch.float32, device="cuda")
+    out, lda = _mat(out, "dA")
+    check(lib.gcs_linear_bwd_input(ptr(dh), ldh, ptr(w), ptr(out), lda, m, k, n, int(accumulate), stream_ptr()),
+          "gcs_linear_bwd_input")
+    return out
+
+
+# ------------------------------------------------------------------ BatchNorm + PReLU (K2/K8)
+def bn_stats(h):
+    torch = _t()
+    lib = _lib.load()
+    h, ldh = _mat(h, "h")
+    m, c = h.shape
+    mean = torch.empty(c, dtype=torch.float32, device="cuda")
+    var = torch.empty(c, dtype=torch.float32, device="cuda")
+    ws = _ws(lib.gcs_bn_workspace_bytes(m, c))
+    check(lib.gcs_bn_stats(ptr(h), ldh, m, c, ptr(mean), ptr(var), ptr(ws), ws.numel(), stream_ptr()), "gcs_bn_stats")
+    return mean, var
+
+
+def bn_fold(mean, var, gamma, beta, eps=1e-3, momentum=0.99, moving_mean=None, moving_var=None):
+    torch = _t()
+    lib = _lib.load()
+    c = mean.shape[0]
+    scale = torch.empty(c, dtype=torch.float32, device="cuda")
+    shift = torch.empty(c, dtype=torch.float32, device="cuda")
+    check(lib.gcs_bn_fold(ptr(mean), ptr(var), ptr(gamma), ptr(beta), eps, momentum, ptr(moving_mean),
+                          ptr(moving_var), ptr(scale), ptr(shift), c, stream_ptr()), "gcs_bn_fold")
+    return scale, shift
+
+
+def bn_prelu_fwd(h, scale, shift, alpha=None, out=None):
+    torch = _t()
+    lib = _lib.load()
+    h, ldh = _mat(h, "h")
+    m, c = h.shape
+    if out is None:
+        out = torch.empty(m, c, dtype=torch.float32, device="cuda")
+    out, ldo = _mat(out, "out")
+    check(lib.gcs_bn_prelu_fwd(ptr(h), ldh, ptr(scale), ptr(shift), ptr(alpha), ptr(out), ldo, m, c, stream_ptr()),
+          "gcs_bn_prelu_fwd")
+    return out
+
+
+def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3):
+    torch = _t()
+    lib = _lib.load()
+    da, ldda = _mat(da, "da")
+    h, ldh = _mat(h, "h")
+    m, c = h.shape
+    dh = torch.empty(m, c, dtype=torch.float32, device="cuda")
+    dgamma = torch.empty(c, dtype=torch.float32, device="cuda")
+    dbeta = torch.empty(c, dtype=torch.float32, device="cuda")
+    dalpha = torch.empty(c, dtype=torch.float32, device="cuda") if alpha is not None else None
+    ws = _ws(lib.gcs_bn_workspace_bytes(m, c))
+    check(lib.gcs_bn_prelu_bwd(ptr(da), ldda, ptr(h), ldh, ptr(mean), ptr(var), ptr(gamma), ptr(beta), ptr(alpha),
+                               eps, ptr(dh), c, ptr(dgamma), ptr(dbeta), ptr(dalpha), m, c, ptr(ws), ws.numel(),
+                               stream_ptr()), "gcs_bn_prelu_bwd")
+    return dh, dgamma, dbeta, dalpha
+
+
+# ------------------------------------------------------------------ aggregation (K3/K7)
+def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, graph_ptr=None,
+             max_graph_rows: int = 0):
+    """Y = pattern(A) . prelu(x*scale + shift, alpha)  (identity prologue when scale is None)."""
+    torch = _t()
+    lib = _lib.load()
+    x, ldx = _mat(x, "x")
+    n, hdim = x.shape
+    if rowptr.shape[0] != n + 1:
+        raise ValueError(f"A has {rowptr.shape[0] - 1} rows but x has {n}")
+    if out is None:
+        out = torch.empty(n, hdim, dtype=torch.float32, device="cuda")
+    out, ldy = _mat(out, "y")
+    n_graphs = graph_ptr.shape[0] - 1 if graph_ptr is not None else 0
+    check(lib.gcs_spmm_sum(ptr(rowptr), ptr(colidx), ptr(graph_ptr), n_graphs, max_graph_rows, n, ptr(x), ldx,
+                           ptr(scale), ptr(shift), ptr(alpha), ptr(out), ldy, hdim, stream_ptr()), "gcs_spmm_sum")
+    return out
+
+
+# ------------------------------------------------------------------ pooling (K4/K6)
+def segment_sum_fwd(x, graph_ptr, out=None):
+    torch = _t()
+    lib = _lib.load()
+    x, ldx = _mat(x, "x")
+    b = graph_ptr.shape[0] - 1
+    w = x.shape[1]
+    if out is None:
+        out = torch.empty(b, w, dtype=torch.float32, device="cuda")
+    out, ldo = _mat(out, "out")
+    check(lib.gcs_segment_sum_fwd(ptr(x), ldx, ptr(graph_ptr), b, w, ptr(out), ldo, stream_ptr()),
+          "gcs_segment_sum_fwd")
+    return out
+
+
+def segment_sum_bwd(dout, graph_ptr, n_nodes: int, out=None):
+    torch = _t()
+    lib = _lib.load()
+    dout, ldo = _mat(dout, "dout")
+    b, w = dout.shape
+    if out is None:
+        out = torch.empty(n_nodes, w, dtype=torch.float32, device="cuda")
+    out, ldx = _mat(out, "dx")
+    check(lib.gcs_segment_sum_bwd(ptr(dout), ldo, ptr(graph_ptr), b, w, ptr(out), ldx, stream_ptr()),
+          "gcs_segment_sum_bwd")
+    return out
+
+
+# ------------------------------------------------------------------ loss (K5) / optimizers (K10)
+def softmax_xent(logits, y=None, grad_scale: Optional[float] = None, want_grad=False):
+    """Returns (probs, loss_acc[2] or None, dlogits or None)."""
+    torch = _t()
+    lib = _lib.load()
+    logits, _ = _mat(logits, "logits")
+    logits = logits.contiguous()
+    b, c = logits.shape
+    probs = torch.empty_like(logits)
+    loss_acc = torch.empty(2, dtype=torch.float32, device="cuda") if y is not None else None
+    dlogits = torch.empty_like(logits) if (want_grad and y is not None) else None
+    if y is not None:
+        y, _ = _mat(y, "y")
+        y = y.contiguous()
+    gs = (1.0 / b if b else 0.0) if grad_scale is None else grad_scale
+    check(lib.gcs_softmax_xent(ptr(logits), ptr(y), b, c, ptr(probs), ptr(loss_acc), ptr(dlogits), gs, stream_ptr()),
+          "gcs_softmax_xent")
+    return probs, loss_acc, dlogits
+
+
+def sgd_step(w, g, lr: float, grad_scale: float = 1.0):
+    lib = _lib.load()
+    check(lib.gcs_sgd_step(ptr(w), ptr(g), w.numel(), lr, grad_scale, stream_ptr()), "gcs_sgd_step")
+
+
+def adam_step(w, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-7, grad_scale: float = 1.0):
+    lib = _lib.load()
+    check(lib.gcs_adam_step(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), lr, beta1, beta2, eps, step, grad_scale,
+                            stream_ptr()), "gcs_adam_step")
