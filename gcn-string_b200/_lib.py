@@ -32,7 +32,7 @@ class Batch(Structure):
 
 
 P = c_void_p
-I32, I64, F32 = c_int32, c_int64, c_float
+I32, I64, F32, F64 = c_int32, c_int64, c_float, ctypes.c_double
 
 # name -> (restype, argtypes); mirrors include/gcnstring_b200.h declaration by declaration.
 PROTOTYPES = {
@@ -59,7 +59,7 @@ PROTOTYPES = {
     "gcs_segment_sum_bwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_softmax_xent": (c_int32, [P, P, I32, I32, P, P, P, F32, P]),
     "gcs_sgd_step": (c_int32, [P, P, I64, F32, F32, P]),
-    "gcs_adam_step": (c_int32, [P, P, P, P, I64, F32, F32, F32, F32, I64, F32, P]),
+    "gcs_adam_step": (c_int32, [P, P, P, P, I64, F64, F64, F64, F64, I64, F32, P]),
     "gcs_model_num_params": (c_int64, [POINTER(ModelConfig)]),
     "gcs_model_num_state": (c_int64, [POINTER(ModelConfig)]),
     "gcs_model_workspace_bytes": (c_int64, [POINTER(ModelConfig), I64, I64, I32, I32]),
@@ -69,7 +69,10 @@ PROTOTYPES = {
     "gcs_model_backward": (c_int32, [POINTER(ModelConfig), P, POINTER(Batch), P, P, P, I64, P]),
 }
 # test/sweep hook, not part of the header
-_DEBUG = {"gcs_debug_set_spmm_mode": (None, [I32])}
+_DEBUG = {"gcs_debug_set_spmm_mode": (None, [I32]),
+          "gcs_debug_launch_count": (ctypes.c_longlong, []),
+          "gcs_debug_profile_begin": (None, []),
+          "gcs_debug_profile_end": (c_int32, [ctypes.c_char_p, c_int32])}
 
 _lib = None
 
@@ -136,3 +139,19 @@ def model_config(cfg) -> ModelConfig:
     return ModelConfig(cfg.in_features, cfg.output, cfg.hidden, cfg.message_passing, cfg.pre_process,
                        cfg.post_process, CONNECTIVITY[cfg.connectivity], POOL[cfg.pool],
                        FINAL_ACT[cfg.activation], cfg.bn_momentum, cfg.bn_epsilon)
+
+
+def profile_begin():
+    load().gcs_debug_profile_begin()
+
+
+def profile_end():
+    """{label: (count, total_ms)} of the ops timed since profile_begin()."""
+    buf = ctypes.create_string_buffer(8192)
+    load().gcs_debug_profile_end(buf, 8192)
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            label, count, ms = item.split(":")
+            out[label] = (int(count), float(ms))
+    return out

@@ -18,6 +18,18 @@ inline cudaStream_t as_stream(gcs_stream s) { return reinterpret_cast<cudaStream
 // Number of SMs on the current device (cached per device).
 int sm_count();
 
+// Count of kernel launches issued by this library (bench.py's `gpu_launches`).
+void count_launch();
+
+// Optional per-op device timing (gcs_debug_profile_*): CUDA events on the launching stream
+// around each op of the model entry points.  Off by default; no cost when off.
+struct ScopedOpTimer {
+  int slot;
+  cudaStream_t st;
+  ScopedOpTimer(const char* label, gcs_stream stream);
+  ~ScopedOpTimer();
+};
+
 #define GCS_CHECK_ARG(cond, ...)                                              \
   do {                                                                        \
     if (!(cond)) return ::gcs::fail(GCS_ERR_INVALID_ARGUMENT, __VA_ARGS__);   \
@@ -28,6 +40,7 @@ int sm_count();
     cudaError_t e__ = cudaGetLastError();                                                   \
     if (e__ != cudaSuccess)                                                                 \
       return ::gcs::fail(GCS_ERR_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+    ::gcs::count_launch();                                                                  \
   } while (0)
 
 #define GCS_CUDA(call)                                                                      \

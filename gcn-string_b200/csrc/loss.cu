@@ -3,6 +3,7 @@
 // :339 accuracy).  Keras recovers the logits of the softmax activation
 // and evaluates softmax_cross_entropy_with_logits:
 //   loss_b = logsumexp(z_b) * sum(y_b) - y_b . z_b ;  loss = mean_b loss_b
+//          (evaluated as log(sum exp(z - m)) * sum(y) - y . (z - m), m = max z)
 //   dz_b   = (softmax(z_b) * sum(y_b) - y_b) * grad_scale
 // One CTA, fixed-order tree reduction: deterministic.  B x C is tiny ([1024, 2]).
 #include "common.cuh"
@@ -26,9 +27,13 @@ __global__ void __launch_bounds__(1024) softmax_xent_kernel(
     for (int c = 1; c < C; ++c)
       if (z[c] > m) { m = z[c]; arg_p = c; }       // first maximum, like tf.argmax
     float e[kMaxClasses];
-    float sum = 0.f;
-    for (int c = 0; c < C; ++c) { e[c] = expf(z[c] - m); sum += e[c]; }
-    const float lse = m + logf(sum);
+    float rest = 0.f;                                // sum over c != argmax; e[argmax] = 1 exactly
+    for (int c = 0; c < C; ++c) {
+      e[c] = expf(z[c] - m);
+      if (c != arg_p) rest += e[c];
+    }
+    const float sum = 1.0f + rest;
+    const float log_sum = log1pf(rest);              // lse = m + log_sum, accurate for confident rows
     const float inv = 1.0f / sum;
     float ysum = 0.f, yz = 0.f, ymax = 0.f;
     int arg_y = 0;
@@ -37,10 +42,10 @@ __global__ void __launch_bounds__(1024) softmax_xent_kernel(
       ymax = yy[0];
       for (int c = 0; c < C; ++c) {
         ysum += yy[c];
-        yz = fmaf(yy[c], z[c], yz);
+        yz = fmaf(yy[c], z[c] - m, yz);            // y . (z - m): no cancellation against lse
         if (c > 0 && yy[c] > ymax) { ymax = yy[c]; arg_y = c; }
       }
-      loss += static_cast<double>(lse * ysum - yz);
+      loss += static_cast<double>(log_sum * ysum - yz);
       hit += (arg_y == arg_p);
     }
     for (int c = 0; c < C; ++c) {

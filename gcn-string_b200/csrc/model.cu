@@ -69,6 +69,12 @@ static int check_config(const gcs_model_config* c) {
   return GCS_OK;
 }
 
+#define GCS_TIMED(label, call)                 \
+  do {                                         \
+    ::gcs::ScopedOpTimer timer__(label, st);   \
+    GCS_TRY(call);                             \
+  } while (0)
+
 // Bump allocator over the caller's workspace; with base == nullptr it only measures.
 struct Arena {
   char* base;
@@ -197,7 +203,7 @@ static int block_norm(const gcs_model_config& c, const Plan& p, int bi, const fl
   float* mm = state + b.stat_off;
   float* mv = mm + b.m_out;
   if (training) {
-    GCS_TRY(gcs_bn_stats(h, ldh, rows, b.m_out, mean, var, p.bn_ws, p.bn_ws_bytes, st));
+    GCS_TIMED("bn_stats", gcs_bn_stats(h, ldh, rows, b.m_out, mean, var, p.bn_ws, p.bn_ws_bytes, st));
     GCS_TRY(gcs_bn_fold(mean, var, params + b.gamma(), params + b.beta(), c.bn_epsilon, c.bn_momentum, mm, mv,
                         scale, shift, b.m_out, st));
   } else {
@@ -217,12 +223,12 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
   int64_t ld_in = bt.ldx;
   for (int j = 0; j < P; ++j) {
     const BlockDesc& b = p.blocks[j];
-    GCS_TRY(gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, st));
+    GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, st));
     GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
     float* out = j < P - 1 ? p.act[j] : p.cat + static_cast<int64_t>(L) * H;
     const int64_t ld_out = j < P - 1 ? H : Wc;
     const float* scale = p.stat[j] + 2 * H;
-    GCS_TRY(gcs_bn_prelu_fwd(p.h[j], H, scale, scale + H, params + b.alpha(), out, ld_out, N, H, st));
+    GCS_TIMED("bn_prelu_fwd", gcs_bn_prelu_fwd(p.h[j], H, scale, scale + H, params + b.alpha(), out, ld_out, N, H, st));
     in = out;
     ld_in = ld_out;
   }
@@ -231,18 +237,18 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     const int bi = P + k;
     const BlockDesc& b = p.blocks[bi];
     const float* cin = p.cat + static_cast<int64_t>(L - k) * H;          // trailing (k+1)*H columns
-    GCS_TRY(gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, st));
+    GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
     const float* scale = p.stat[bi] + 2 * H;
-    GCS_TRY(gcs_spmm_sum(bt.rowptr, bt.colidx, bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, N, p.h[bi], H,
-                         scale, scale + H, params + b.alpha(), p.cat + static_cast<int64_t>(L - k - 1) * H, Wc,
-                         H, st));
+    GCS_TIMED("spmm_fwd", gcs_spmm_sum(bt.rowptr, bt.colidx, bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, N,
+                                       p.h[bi], H, scale, scale + H, params + b.alpha(),
+                                       p.cat + static_cast<int64_t>(L - k - 1) * H, Wc, H, st));
   }
   // global sum pool
   const float* pin = p.cat;
   int64_t ld_pin = Wc;
   if (c.pool) {
-    GCS_TRY(gcs_segment_sum_fwd(p.cat, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.pooled, Wc, st));
+    GCS_TIMED("pool_fwd", gcs_segment_sum_fwd(p.cat, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.pooled, Wc, st));
     pin = p.pooled;
   }
   // post-processing MLP
@@ -275,14 +281,16 @@ static int block_backward(const gcs_model_config& c, const Plan& p, int bi, cons
   const BlockDesc& b = p.blocks[bi];
   const float* mean = p.stat[bi];
   const float* var = mean + b.m_out;
-  GCS_TRY(gcs_bn_prelu_bwd(da, ldda, h, ldh, mean, var, params + b.gamma(), params + b.beta(),
-                           b.has_alpha ? params + b.alpha() : nullptr, c.bn_epsilon, dh, lddh, grads + b.gamma(),
-                           grads + b.beta(), b.has_alpha ? grads + b.alpha() : nullptr, rows, b.m_out, p.bn_ws,
-                           p.bn_ws_bytes, st));
-  GCS_TRY(gcs_linear_bwd_weight(in, ld_in, dh, lddh, grads + b.kernel(), grads + b.bias(), rows, b.k_in, b.m_out,
-                                p.lw_ws, p.lw_ws_bytes, st));
+  GCS_TIMED("bn_prelu_bwd", gcs_bn_prelu_bwd(da, ldda, h, ldh, mean, var, params + b.gamma(), params + b.beta(),
+                                             b.has_alpha ? params + b.alpha() : nullptr, c.bn_epsilon, dh, lddh,
+                                             grads + b.gamma(), grads + b.beta(),
+                                             b.has_alpha ? grads + b.alpha() : nullptr, rows, b.m_out, p.bn_ws,
+                                             p.bn_ws_bytes, st));
+  GCS_TIMED("linear_bwd_weight", gcs_linear_bwd_weight(in, ld_in, dh, lddh, grads + b.kernel(), grads + b.bias(), rows,
+                                                       b.k_in, b.m_out, p.lw_ws, p.lw_ws_bytes, st));
   if (din)
-    GCS_TRY(gcs_linear_bwd_input(dh, lddh, params + b.kernel(), din, lddin, rows, b.k_in, b.m_out, accumulate, st));
+    GCS_TIMED("linear_bwd_input", gcs_linear_bwd_input(dh, lddh, params + b.kernel(), din, lddin, rows, b.k_in,
+                                                       b.m_out, accumulate, st));
   return GCS_OK;
 }
 
@@ -310,13 +318,13 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
     ldda = lddin;
   }
   // ---- pool: dX[n] = dOut[i[n]]
-  if (c.pool) GCS_TRY(gcs_segment_sum_bwd(p.dpooled, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.gcat, Wc, st));
+  if (c.pool) GCS_TIMED("pool_bwd", gcs_segment_sum_bwd(p.dpooled, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.gcat, Wc, st));
   // ---- message passing, last layer first; skip gradients accumulate into gcat in place
   for (int k = L - 1; k >= 0; --k) {
     const int bi = P + k;
     const float* dz = p.gcat + static_cast<int64_t>(L - k - 1) * H;
-    GCS_TRY(gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, N, dz, Wc,
-                         nullptr, nullptr, nullptr, p.tmp_a, H, H, st));
+    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, N, dz,
+                                       Wc, nullptr, nullptr, nullptr, p.tmp_a, H, H, st));
     GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N,
                            p.cat + static_cast<int64_t>(L - k) * H, Wc, p.tmp_b, H,
                            p.gcat + static_cast<int64_t>(L - k) * H, Wc, 1, st));

@@ -19,13 +19,13 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ w, const f
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                   float lr_t, float beta1, float beta2, float eps,
-                                                   float grad_scale) {
+                                                   float lr_t, float beta1, float beta2, float omb1,
+                                                   float omb2, float eps, float grad_scale) {
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float gk = g[k] * grad_scale;
-    const float mk = beta1 * m[k] + (1.0f - beta1) * gk;
-    const float vk = beta2 * v[k] + (1.0f - beta2) * gk * gk;
+    const float mk = beta1 * m[k] + omb1 * gk;
+    const float vk = beta2 * v[k] + omb2 * gk * gk;
     m[k] = mk;
     v[k] = vk;
     w[k] = w[k] - lr_t * mk / (sqrtf(vk) + eps);
@@ -50,14 +50,17 @@ extern "C" int gcs_sgd_step(float* w, const float* g, int64_t n, float lr, float
   return GCS_OK;
 }
 
-extern "C" int gcs_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                             float beta2, float eps, int64_t step, float grad_scale, gcs_stream stream) {
+extern "C" int gcs_adam_step(float* w, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                             double beta2, double eps, int64_t step, float grad_scale, gcs_stream stream) {
   GCS_CHECK_ARG(n >= 0 && step >= 1 && (n == 0 || (w && g && m && v)), "gcs_adam_step: bad argument (step is 1-based)");
   if (n == 0) return GCS_OK;
   const double t = static_cast<double>(step);
-  const float lr_t = static_cast<float>(static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), t)) /
-                                        (1.0 - pow(static_cast<double>(beta1), t)));
-  adam_kernel<<<opt_blocks(n), 256, 0, as_stream(stream)>>>(w, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+  // hyper-parameters arrive as doubles so that 1 - beta is rounded once, not computed in fp32
+  const float lr_t = static_cast<float>(lr * sqrt(1.0 - pow(beta2, t)) / (1.0 - pow(beta1, t)));
+  adam_kernel<<<opt_blocks(n), 256, 0, as_stream(stream)>>>(w, g, m, v, n, lr_t, static_cast<float>(beta1),
+                                                            static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
+                                                            static_cast<float>(1.0 - beta2), static_cast<float>(eps),
+                                                            grad_scale);
   GCS_CHECK_LAUNCH("adam_kernel");
   return GCS_OK;
 }

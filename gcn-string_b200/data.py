@@ -219,6 +219,105 @@ class DeviceGraphStore:
         return x, a, seg, y
 
 
+class HostGraphStore:
+    """Streaming variant: the packed dataset stays in PINNED host memory and every step uploads
+    only the graphs of its batch (host -> device copies inside the step), then runs the same
+    device batching kernel on the uploaded slices.  Consecutive graph ids (shuffle=False) are
+    uploaded as zero-copy slices; a shuffled batch is first gathered into a pinned staging
+    buffer on the host."""
+
+    def __init__(self, packed: PackedGraphs, symmetric: Optional[bool] = None):
+        torch = _lib.require_cuda()
+        _lib.load()
+        self.n_graphs = packed.n_graphs
+        self.n_feat = int(packed.x.shape[1])
+        self.n_classes = int(packed.y.shape[1]) if packed.y.ndim == 2 else 0
+        self.h_n_nodes = packed.n_nodes.astype(np.int64)
+        self.h_n_edges = packed.n_edges.astype(np.int64)
+        self.h_node_off = packed.node_off
+        self.h_rowptr = packed.rowptr
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+        self.node_off, self.rowptr, self.col = pin(packed.node_off), pin(packed.rowptr), pin(packed.col)
+        self.x = pin(packed.x.astype(np.float32, copy=False))
+        self.y = pin(packed.y.astype(np.float32, copy=False)) if self.n_classes else None
+        self.symmetric = symmetric
+        self.h2d_bytes_last = 0
+
+    def _gather(self, ids):
+        """Pack the graphs ``ids`` (any order) into a fresh pinned mini-dataset."""
+        torch = _lib.require_cuda()
+        sub = PackedGraphs(*_take_graphs(self, ids))
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+        return pin(sub.node_off), pin(sub.rowptr), pin(sub.col), pin(sub.x), (pin(sub.y) if self.n_classes else None)
+
+    def batch(self, graph_ids_dev, graph_ids_host, want_coo=False, want_labels=True):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        ids = np.asarray(graph_ids_host, dtype=np.int64)
+        b = int(ids.shape[0])
+        consecutive = b > 0 and np.array_equal(ids, np.arange(ids[0], ids[0] + b))
+        if consecutive:
+            g0, g1 = int(ids[0]), int(ids[0]) + b
+            n0, n1 = int(self.h_node_off[g0]), int(self.h_node_off[g1])
+            e0, e1 = int(self.h_rowptr[n0]), int(self.h_rowptr[n1])
+            parts = (self.node_off[g0:g1 + 1], self.rowptr[n0:n1 + 1], self.col[e0:e1], self.x[n0:n1],
+                     self.y[g0:g1] if self.y is not None else None)
+            ids_local = torch.arange(g0, g1, dtype=torch.int64)
+        else:
+            parts = self._gather(ids)
+            g0 = n0 = e0 = 0
+            ids_local = torch.arange(0, b, dtype=torch.int64)
+        dev = [t.cuda(non_blocking=True) if t is not None else None for t in parts]
+        ids_dev = ids_local.pin_memory().cuda(non_blocking=True)
+        self.h2d_bytes_last = sum(t.numel() * t.element_size() for t in parts if t is not None) + ids_local.numel() * 8
+        d_node_off, d_rowptr, d_col, d_x, d_y = dev
+        n = int(self.h_n_nodes[ids].sum())
+        nnz = int(self.h_n_edges[ids].sum())
+        max_nodes = int(self.h_n_nodes[ids].max()) if b else 0
+        i32 = dict(dtype=torch.int32, device="cuda")
+        graph_ptr, edge_ptr = torch.empty(b + 1, **i32), torch.empty(b + 1, **i32)
+        rowptr, colidx = torch.empty(n + 1, **i32), torch.empty(nnz, **i32)
+        x = torch.empty(n, self.n_feat, dtype=torch.float32, device="cuda")
+        seg = torch.empty(n, dtype=torch.int64, device="cuda")
+        y = torch.empty(b, self.n_classes, dtype=torch.float32, device="cuda") if (want_labels and d_y is not None) else None
+        coo = torch.empty(nnz, 2, dtype=torch.int64, device="cuda") if want_coo else None
+        flag = torch.zeros(1, **i32)
+        # the uploaded slices are addressed with DATASET-global ids: rebase the pointers instead
+        # of the index arrays (the kernel only touches [g0, g1], [n0, n1], [e0, e1))
+        check(lib.gcs_batch_disjoint(ptr(d_node_off) - 8 * g0, ptr(d_rowptr) - 8 * n0, ptr(d_col) - 4 * e0,
+                                     ptr(d_x) - 4 * self.n_feat * n0,
+                                     (ptr(d_y) - 4 * self.n_classes * g0) if d_y is not None else None,
+                                     self.n_feat, max(self.n_classes, 1), ptr(ids_dev), b, n, nnz, ptr(graph_ptr),
+                                     ptr(edge_ptr), ptr(rowptr), ptr(colidx), ptr(x), ptr(seg), ptr(y), ptr(coo),
+                                     ptr(flag), stream_ptr()), "gcs_batch_disjoint")
+        a = SparseAdjacency(rowptr, colidx, n, graph_ptr=graph_ptr, max_graph_nodes=max_nodes, indices=coo,
+                            symmetric=self.symmetric)
+        a.edge_ptr, a.status = edge_ptr, flag
+        a._keep = (dev, ids_dev)
+        return x, a, seg, y
+
+
+def _take_graphs(store, ids):
+    """Host gather of whole graphs into a packed mini-dataset (node_off, rowptr, col, x, y)."""
+    node_off = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum(store.h_n_nodes[ids], out=node_off[1:])
+    hn, hr = store.h_node_off, store.h_rowptr
+    col_np, x_np = store.col.numpy(), store.x.numpy()
+    rp_np = store.rowptr.numpy()
+    rps, cols, xs = [], [], []
+    e_off = 0
+    for g in ids:
+        n0, n1 = int(hn[g]), int(hn[g + 1])
+        e0, e1 = int(hr[n0]), int(hr[n1])
+        rps.append(rp_np[n0:n1] - e0 + e_off)
+        cols.append(col_np[e0:e1])
+        xs.append(x_np[n0:n1])
+        e_off += e1 - e0
+    rowptr = np.concatenate(rps + [np.array([e_off], dtype=np.int64)])
+    y = store.y.numpy()[ids] if store.y is not None else np.zeros((len(ids), 0), np.float32)
+    return node_off, rowptr, np.concatenate(cols), np.concatenate(xs), y
+
+
 class _Spec:
     """Stand-in for tf.TensorSpec / tf.SparseTensorSpec in ``tf_signature()``."""
 
@@ -236,20 +335,22 @@ class DisjointLoader:
     Batch order follows upstream's ``batch_generator``: per epoch an in-place
     ``np.random.shuffle`` (cumulative across epochs, global NumPy RNG), then consecutive
     slices of ``batch_size``; the last batch may be short; ``steps_per_epoch =
-    ceil(len / batch_size)``.  ``dataset`` may be a ``Dataset``, a list of ``Graph`` or an
+    ceil(len / batch_size)``.  With ``device_resident=False`` the dataset stays in pinned host
+    memory and each step uploads its own graphs.  ``dataset`` may be a ``Dataset``, a list of ``Graph`` or an
     already packed ``PackedGraphs``.  ``rank`` / ``world_size`` shard every global batch by
     graph across data-parallel ranks (rank r takes the r-th contiguous part of the slice).
     """
 
     def __init__(self, dataset, node_level=False, batch_size=1, epochs=None, shuffle=True, rank=0, world_size=1,
-                 want_coo=False, symmetric=None):
+                 want_coo=False, symmetric=None, device_resident=True):
         if node_level:
             raise NotImplementedError("node_level=True labels are not built (reference uses graph labels)")
         packed = dataset if isinstance(dataset, PackedGraphs) else pack_graphs(list(dataset))
         if packed.n_graphs == 0:
             raise ValueError("Datasets cannot be empty")
         self.dataset = dataset
-        self.store = DeviceGraphStore(packed, symmetric=symmetric)
+        # device_resident=False keeps the dataset in pinned host memory and uploads per batch
+        self.store = (DeviceGraphStore if device_resident else HostGraphStore)(packed, symmetric=symmetric)
         self.node_level = node_level
         self.batch_size = int(batch_size)
         self.epochs = epochs

@@ -1,0 +1,80 @@
+"""Data-parallel training: graphs shard across GPUs, one gradient all-reduce per step.
+
+The reference is single-process, single-device (no tf.distribute, no NCCL);
+this is the sharding BASELINE.json's north_star asks for.  A disjoint batch is block-diagonal:
+no edge crosses graphs, pooling is per graph, the loss is a mean over graphs —
+so each rank batches ITS graphs on its GPU and runs forward/backward locally, and the only
+collective is one ``all_reduce(SUM)`` over the flat fp32 gradient buffer (4.26 MB at hidden
+256) through torch.distributed (NCCL over NVLink; gloo on CPU in the tests).
+
+Scaling of the mean loss: every rank back-propagates with grad_scale = 1 / global_batch
+(graphs over ALL ranks), so the summed gradient is the gradient of the mean loss over the
+global batch, also when shards are unequal (short last batch).
+
+BatchNorm statistics stay replica-local (the all-reduce is the only collective): a G-GPU
+step equals G reference steps on the shards with count-weighted gradient averaging, not one
+reference step on the union.  Moving statistics are rank-local; rank 0's are the ones
+``get_weights`` reports after ``sync_state``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+
+def world():
+    """(rank, world_size) from torch.distributed if initialised, else (0, 1)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(start: int, stop: int, rank: int, world_size: int):
+    """Contiguous part of the global batch slice [start, stop) owned by ``rank`` (same rule as
+    data.DisjointLoader): sizes differ by at most one graph, lower ranks take the remainder."""
+    n = stop - start
+    base, rem = divmod(n, world_size)
+    lo = start + rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_gradients(flat_grads, group=None):
+    """In-place SUM all-reduce of the flat gradient bucket (no-op for a single process)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return flat_grads
+
+
+def broadcast_parameters(model, src: int = 0, group=None):
+    """Make every replica start from rank ``src``'s parameters and BatchNorm state."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(model.params, src=src, group=group)
+        dist.broadcast(model.state, src=src, group=group)
+
+
+class DataParallelTrainer:
+    """train_step = local fused forward/backward (grad_scale = 1/global_batch) -> one flat
+    all-reduce -> fused optimizer step, identical on every rank."""
+
+    def __init__(self, model, optimizer, group=None):
+        self.model, self.optimizer, self.group = model, optimizer, group
+        self._synced = False
+
+    def train_step(self, inputs, target, global_batch: Optional[int] = None):
+        rank, ws = world()
+        if not self._synced and self.model.built:
+            broadcast_parameters(self.model, 0, self.group)
+            self._synced = True
+        a = inputs[1]
+        if global_batch is None:
+            global_batch = getattr(a, "global_batch_graphs", None) or target.shape[0] * ws
+        loss_acc, probs = self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch))
+        if not self._synced:                      # first call built the model lazily
+            broadcast_parameters(self.model, 0, self.group)
+            self._synced = True
+            loss_acc, probs = self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch))
+        allreduce_gradients(self.model.grads, self.group)
+        self.optimizer.apply_flat(self.model.params, self.model.grads)
+        return loss_acc, probs

@@ -166,8 +166,8 @@ int gcs_softmax_xent(const float* logits, const float* y, int32_t B, int32_t C, 
  *   adam: Keras Adam, lr_t = lr*sqrt(1-b2^t)/(1-b1^t), w -= lr_t*m/(sqrt(v)+eps)
  * --------------------------------------------------------------------------------- */
 int gcs_sgd_step(float* w, const float* g, int64_t n, float lr, float grad_scale, gcs_stream stream);
-int gcs_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                  float beta2, float eps, int64_t step, float grad_scale, gcs_stream stream);
+int gcs_adam_step(float* w, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, float grad_scale, gcs_stream stream);
 
 /* ---------------------------------------------------------------------------------
  * Whole-model entry points: spektral.models.GeneralGNN.__call__ (gcn.py:334 training,

@@ -1,0 +1,290 @@
+"""GPU parity of the whole GeneralGNN path (C-ABI model entry points and the Spektral-style
+Python surface) against the oracle and the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import gcn_string_b200 as g
+from gcn_string_b200 import synthetic
+from gcn_string_b200.params import GNNConfig, block_specs, named_slices
+from oracle import batching_ref, model_ref_np as O1, model_ref_torch as O2
+
+from conftest import ROOT, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5           # BASELINE.json: within 1e-5 relative (fp32) for logits, losses, gradients
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+class _Sparse:
+    """A plain SparseTensor-like triple (what Spektral's loader hands the reference)."""
+
+    def __init__(self, indices, n):
+        self.indices = torch.from_numpy(indices).cuda()
+        self.values = torch.ones(indices.shape[0], dtype=torch.int64, device="cuda")
+        self.dense_shape = (n, n)
+
+
+def make_model(cfg, w, s):
+    kw = dict(hidden=cfg.hidden, message_passing=cfg.message_passing, pre_process=cfg.pre_process,
+              post_process=cfg.post_process, pool=cfg.pool)
+    m = g.GeneralGNN(cfg.output, activation=cfg.activation, **kw)
+    m.build(cfg.in_features)
+    m.load_flat(w, s)
+    return m
+
+
+def grad_errors(got, ref, cfg):
+    """{tensor name: max-abs error / max(|tensor|_inf, 0.1 * |all grads|_inf)}.  The floor puts
+    mathematically-zero gradients (every bias in front of a BatchNorm) on the scale of the rest."""
+    floor = 0.1 * np.abs(ref).max()
+    out = {}
+    for name, shape, off, buf in named_slices(cfg):
+        if buf == "trainable":
+            n = int(np.prod(shape))
+            out[name] = np.abs(got[off:off + n] - ref[off:off + n]).max() / max(np.abs(ref[off:off + n]).max(), floor)
+    return out
+
+
+def assert_grads_close(got, ref, cfg, fp32_ref=None, tol=TOL):
+    """Per-tensor 1e-5 relative, or 4x the error the float32 CPU restatement (O2) itself makes
+    against the float64 oracle where that fp32 noise floor is higher (tiny-batch BatchNorm)."""
+    e_gpu = grad_errors(got, ref, cfg)
+    e_o2 = grad_errors(fp32_ref, ref, cfg) if fp32_ref is not None else {}
+    bad = {k: (v, e_o2.get(k)) for k, v in e_gpu.items() if v > max(tol, 4 * e_o2.get(k, 0.0))}
+    assert not bad, f"gradient tensors out of tolerance (gpu err, fp32-cpu err): {bad}"
+
+
+@pytest.mark.parametrize("name", ["tiny_h8", "small_h32"])
+def test_golden_vectors(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    F, C, H, L = (int(v) for v in z["cfg"])
+    cfg = GNNConfig(in_features=F, output=C, activation="softmax", hidden=H, message_passing=L)
+    nb = z["y"].shape[0]
+    # device batching from the packed fixture reproduces the fixture's integer structure
+    ds = synthetic.PackedGraphs(z["node_off"], z["ds_rowptr"], z["ds_col"], z["ds_x"], z["ds_y"])
+    loader = g.DisjointLoader(ds, batch_size=nb, epochs=1, shuffle=False, want_coo=True)
+    (x, a, i), y = next(loader)
+    assert np.array_equal(host(a.indices), z["indices"]) and np.array_equal(host(i), z["seg"])
+    assert np.array_equal(host(a.rowptr), z["rowptr"]) and np.array_equal(host(a.colidx), z["colidx"])
+    assert np.array_equal(host(a.graph_ptr), z["graph_ptr"])
+    model = make_model(cfg, z["w"], z["s"])
+    p_inf = model([x, a, i], training=False)
+    assert rel_err(host(p_inf), z["probs_infer"]) < TOL
+    loss_acc, probs = model.train_step_grads([x, a, i], y)
+    la = host(loss_acc)
+    assert abs(la[0] - float(z["loss"])) < TOL * abs(float(z["loss"])) and abs(la[1] - float(z["acc"])) < 1e-6
+    assert rel_err(host(probs), z["probs_train"]) < TOL
+    o2 = O2.loss_and_grads(cfg, block_specs(cfg), z["w"], z["s"], z["x"], z["indices"][:, 0], z["indices"][:, 1],
+                           z["seg"], z["y"], nb)
+    assert_grads_close(host(model.grads), z["grads"], cfg, o2["grads"])
+    assert rel_err(host(model.state), z["new_state"]) < TOL
+
+
+@pytest.mark.parametrize("smooth", [True, False])
+def test_forward_backward_hidden256_cfg1_slice(smooth):
+    """Default architecture (hidden 256, 4 layers) on 8 E. coli-shaped graphs (~500 nodes).
+
+    PReLU's derivative jumps at 0.  Among the ~6M activation inputs here a few lie within fp32
+    rounding of 0, take the other branch in ANY float32 implementation and move a gradient
+    column by O(1e-4) relative - measured: this path 4e-4, while with alpha = 1 (no kink, same
+    kernels, same sizes) it agrees to 2e-6 (scripts/diag_parity.py).  So the strict 1e-5
+    gradient check runs with alpha = 1; with random slopes logits/loss/statistics are still
+    held to 1e-5 and the gradients to the kink-limited bound."""
+    ds = synthetic.make_dataset(8, seed=0, n_mean=500, deg=12, n_feat=32)
+    graphs = [ds.graph(k) for k in range(8)]
+    (xr, (idx, _, _), seg), yr = batching_ref.collate(graphs)
+    cfg = GNNConfig(in_features=32, output=2, activation="softmax")
+    w, s = g.init_params(cfg, seed=4, perturb=True)
+    if smooth:
+        for b in block_specs(cfg):
+            o, n = b.alpha
+            w[o:o + n] = 1.0
+    ref = O1.loss_and_grads(cfg, block_specs(cfg), w, s, xr, idx[:, 0], idx[:, 1], seg, yr, 8)
+    loader = g.DisjointLoader(ds, batch_size=8, epochs=1, shuffle=False)
+    (x, a, i), y = next(loader)
+    model = make_model(cfg, w, s)
+    loss_acc, probs = model.train_step_grads([x, a, i], y)
+    assert abs(host(loss_acc)[0] - ref["loss"]) < TOL * abs(ref["loss"])
+    assert rel_err(host(probs), ref["probs"]) < TOL
+    assert rel_err(host(model.state), ref["new_state"]) < TOL
+    got = host(model.grads)
+    if smooth:
+        assert_grads_close(got, ref["grads"], cfg)
+        assert rel_err(got, ref["grads"]) < TOL
+    else:
+        assert rel_err(got, ref["grads"]) < 5e-3
+        assert np.linalg.norm(got - ref["grads"]) / np.linalg.norm(ref["grads"]) < 1e-3
+    # run-to-run determinism: bitwise identical gradients
+    g1 = model.grads.clone()
+    model.load_flat(w, s)
+    model.train_step_grads([x, a, i], y)
+    assert torch.equal(g1, model.grads)
+
+
+def test_random_small_cases_away_from_the_prelu_kink():
+    """Random slopes, strict tolerance: small cases redrawn until every PReLU input is at least
+    2e-5 from 0 (20x the fp32 error of a PReLU input here; the conditioning rule of
+    tests/golden/make_golden.py, which uses 2e-4)."""
+    done = 0
+    for seed in range(40):
+        ds = synthetic.make_dataset(5, seed=100 + seed, n_mean=40, deg=6, n_feat=9)
+        (xr, (idx, _, _), seg), yr = batching_ref.collate([ds.graph(k) for k in range(5)])
+        cfg = GNNConfig(in_features=9, output=2, activation="softmax", hidden=24, message_passing=3)
+        specs = block_specs(cfg)
+        w, s = g.init_params(cfg, seed=seed, perturb=True)
+        ref = O1.loss_and_grads(cfg, specs, w, s, xr, idx[:, 0], idx[:, 1], seg, yr, 5)
+        if min(np.abs(c["z"]).min() for c, b in zip(ref["ctx"]["caches"], specs) if b.has_alpha) < 2e-5:
+            continue
+        o2 = O2.loss_and_grads(cfg, specs, w, s, xr, idx[:, 0], idx[:, 1], seg, yr, 5)
+        (x, a, i), y = next(g.DisjointLoader(ds, batch_size=5, epochs=1, shuffle=False))
+        model = make_model(cfg, w, s)
+        loss_acc, probs = model.train_step_grads([x, a, i], y)
+        assert abs(host(loss_acc)[0] - ref["loss"]) < TOL * abs(ref["loss"])
+        assert rel_err(host(probs), ref["probs"]) < TOL
+        assert_grads_close(host(model.grads), ref["grads"], cfg, o2["grads"])
+        done += 1
+        if done == 3:
+            break
+    assert done == 3
+
+
+def test_spektral_style_inputs_and_layers(small_case):
+    c = small_case
+    cfg, n = c["cfg"], c["x"].shape[0]
+    model = make_model(cfg, c["w"], c["s"])
+    a = _Sparse(c["idx"], n)
+    x64 = torch.from_numpy(c["x"].astype(np.float64)).cuda()          # f64 features, as MyDataset emits
+    i = torch.from_numpy(c["seg"]).cuda()
+    rows, cols = c["idx"][:, 0], c["idx"][:, 1]
+    ref, _ = O1.forward(cfg, c["specs"], c["w"], c["s"], c["x"].astype(np.float32), rows, cols, c["seg"], 8, False)
+    out = model([x64, a, i], training=False)
+    assert out.shape == (8, 2) and rel_err(host(out), ref) < TOL
+    assert rel_err(host(model([x64, a, i[:, None]])), ref) < TOL       # rank-2 batch index
+    with pytest.raises(AssertionError, match="SparseTensor"):
+        model([x64, torch.zeros(n, n), i])
+    with pytest.raises(ValueError):
+        model([x64[:, :5], a, i])
+    # [x, a] without a batch index: one graph, pool over all nodes
+    one = model([x64, a])
+    ref1, _ = O1.forward(cfg, c["specs"], c["w"], c["s"], c["x"].astype(np.float32), rows, cols,
+                         np.zeros(n, dtype=np.int64), 1, False)
+    assert one.shape == (1, 2) and rel_err(host(one), ref1) < TOL
+    # GlobalSumPool / GeneralConv layers on their own
+    xs = torch.from_numpy(c["x"].astype(np.float32)).cuda()
+    pooled = g.GlobalSumPool()([xs, i])
+    assert rel_err(host(pooled), O1.segment_sum(c["x"].astype(np.float64), c["seg"], 8)) < TOL
+    conv = g.GeneralConv(channels=16, seed=3)
+    z = conv([xs, a])
+    blk = conv.block
+    h = c["x"].astype(np.float64) @ host(blk.kernel).astype(np.float64)
+    act = h / np.sqrt(1 + 1e-3)                                        # fresh BN (moving stats 0/1), alpha = 0
+    act = np.where(act > 0, act, 0.0)
+    assert z.shape == (n, 16) and rel_err(host(z), O1.spmm_sum(rows, cols, act, n)) < TOL
+
+
+def test_node_level_output_without_pooling(small_case):
+    c = small_case
+    cfg = GNNConfig(in_features=12, output=3, activation=None, hidden=16, message_passing=2, pool=None)
+    w, s = g.init_params(cfg, seed=8, perturb=True)
+    model = make_model(cfg, w, s)
+    n = c["x"].shape[0]
+    out = model([torch.from_numpy(c["x"].astype(np.float32)).cuda(), _Sparse(c["idx"], n)])
+    ref, _ = O1.forward(cfg, block_specs(cfg), w, s, c["x"].astype(np.float32), c["idx"][:, 0], c["idx"][:, 1],
+                        c["seg"], 8, False)
+    assert out.shape == (n, 3) and rel_err(host(out), ref) < TOL
+
+
+def test_gradient_tape_training_loop_matches_oracle(small_case):
+    """The reference's train_step (gcn.py:328-340) written against this package, three SGD
+    steps with the reference's PiecewiseConstantDecay, against the oracle's weights."""
+    c = small_case
+    cfg, specs = c["cfg"], c["specs"]
+    model = make_model(cfg, c["w"], c["s"])
+    loader = g.DisjointLoader(c["ds"], batch_size=8, epochs=3, shuffle=False)
+    sched = g.optimizers.schedules.PiecewiseConstantDecay([0, 1], [0.02, 0.002, 0.0002])
+    optimizer = g.optimizers.SGD(learning_rate=sched)
+    loss_fn = g.CategoricalCrossentropy()
+    w_ref, s_ref = c["w"].astype(np.float64), c["s"].astype(np.float64)
+    rows, cols = c["idx"][:, 0], c["idx"][:, 1]
+    step = 0
+    for inputs, target in loader:
+        with g.GradientTape() as tape:
+            predictions = model(inputs, training=True)
+            loss = loss_fn(target, predictions) + sum(model.losses)
+        gradients = tape.gradient(loss, model.trainable_variables)
+        optimizer.apply_gradients(zip(gradients, model.trainable_variables))
+        acc = g.categorical_accuracy(target, predictions).mean()
+        r = O1.loss_and_grads(cfg, specs, w_ref, s_ref, c["x"], rows, cols, c["seg"], c["y"], 8)
+        assert abs(float(loss) - r["loss"]) < TOL * abs(r["loss"]) and abs(float(acc) - r["acc"]) < 1e-6
+        w_ref = O1.sgd_step(w_ref, r["grads"], O1.piecewise_constant(step, [0, 1], [0.02, 0.002, 0.0002]))
+        s_ref = r["new_state"]
+        step += 1
+    assert step == 3 and optimizer.iterations == 3
+    assert rel_err(host(model.params), w_ref) < TOL and rel_err(host(model.state), s_ref) < TOL
+    named = model.get_named_weights()
+    assert len(model.get_weights()) == len(named) and "gnn.0.kernel" in named
+    # evaluation path (gcn.py:342-362): inference-mode loss from the attached logits
+    inputs, target = next(g.DisjointLoader(c["ds"], batch_size=8, epochs=1, shuffle=False))
+    pred = model(inputs, training=False)
+    p_ref, ctx = O1.forward(cfg, specs, w_ref, s_ref, c["x"], rows, cols, c["seg"], 8, False)
+    l_ref, _ = O1.xent_from_logits(ctx["logits"], c["y"].astype(np.float64))
+    assert abs(float(loss_fn(target, pred)) - l_ref) < TOL * abs(l_ref)
+
+
+def test_adam_training_matches_oracle(small_case):
+    c = small_case
+    cfg, specs = c["cfg"], c["specs"]
+    model = make_model(cfg, c["w"], c["s"])
+    opt = g.optimizers.Adam(learning_rate=1e-3)
+    (x, a, i), y = next(g.DisjointLoader(c["ds"], batch_size=8, epochs=1, shuffle=False))
+    w_ref, s_ref = c["w"].astype(np.float64), c["s"].astype(np.float64)
+    m = np.zeros_like(w_ref)
+    v = np.zeros_like(w_ref)
+    for t in range(1, 4):
+        model.train_step_grads([x, a, i], y)
+        opt.apply_flat(model.params, model.grads)
+        r = O1.loss_and_grads(cfg, specs, w_ref, s_ref, c["x"], c["idx"][:, 0], c["idx"][:, 1], c["seg"], c["y"], 8)
+        w_ref, m, v = O1.adam_step(w_ref, r["grads"], m, v, t, 1e-3)
+        s_ref = r["new_state"]
+    # Adam normalises each gradient by its own running magnitude, so the biases in front of a
+    # BatchNorm (true gradient 0, rounding noise in any implementation) move by +-lr at random:
+    # compare every other tensor.
+    got = host(model.params)
+    for name, shape, off, buf in named_slices(cfg):
+        if buf == "trainable" and not name.endswith(".bias"):
+            n = int(np.prod(shape))
+            assert rel_err(got[off:off + n], w_ref[off:off + n]) < 5 * TOL, name
+
+
+def test_loader_epochs_shuffle_and_short_last_batch():
+    ds = synthetic.make_dataset(10, seed=1, n_mean=30, deg=4, n_feat=3)
+    loader = g.DisjointLoader(ds, batch_size=4, epochs=2, shuffle=True)
+    assert loader.steps_per_epoch == 3
+    np.random.seed(123)
+    sizes, seen = [], []
+    for (x, a, i), y in loader:
+        sizes.append(y.shape[0])
+        assert int(i.max()) + 1 == y.shape[0] and x.shape[0] == a.n_rows == i.shape[0]
+        seen.append(host(y))
+    assert sizes == [4, 4, 2, 4, 4, 2]
+    np.random.seed(123)                                   # same permutation upstream would draw
+    order = np.arange(10)
+    np.random.shuffle(order)
+    assert np.array_equal(np.concatenate(seen[:3]), ds.y[order])
+    sig = loader.tf_signature()
+    assert sig[0][0].shape == (None, 3) and sig[0][1].sparse and sig[1].shape == (None, 2)
+    # data-parallel sharding: the ranks' shards tile the global batch in order
+    parts = []
+    for r in range(2):
+        ld = g.DisjointLoader(ds, batch_size=5, epochs=1, shuffle=False, rank=r, world_size=2)
+        parts.append([host(y) for (_, _, _), y in ld])
+    assert np.array_equal(np.concatenate([parts[0][0], parts[1][0]]), ds.y[:5])
+    assert parts[0][0].shape[0] == 3 and parts[1][0].shape[0] == 2
