@@ -26,9 +26,10 @@ class ModelConfig(Structure):
 
 
 class Batch(Structure):
-    _fields_ = [("n_nodes", c_int64), ("nnz", c_int64), ("n_graphs", c_int32), ("max_graph_nodes", c_int32),
+    _fields_ = [("n_nodes", c_int64), ("nnz", c_int64), ("n_graphs", c_int32), ("reserved", c_int32),
                 ("rowptr", c_void_p), ("colidx", c_void_p), ("rowptr_t", c_void_p), ("colidx_t", c_void_p),
-                ("graph_ptr", c_void_p), ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p)]
+                ("graph_ptr", c_void_p), ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p),
+                ("tile_ptr", c_void_p), ("n_tiles_dev", c_void_p)]
 
 
 P = c_void_p
@@ -54,7 +55,9 @@ PROTOTYPES = {
     "gcs_bn_fold": (c_int32, [P, P, P, P, F32, F32, P, P, P, P, I32, P]),
     "gcs_bn_prelu_fwd": (c_int32, [P, I64, P, P, P, P, I64, I64, I32, P]),
     "gcs_bn_prelu_bwd": (c_int32, [P, I64, P, I64, P, P, P, P, P, F32, P, I64, P, P, P, I64, I32, P, I64, P]),
-    "gcs_spmm_sum": (c_int32, [P, P, P, I32, I32, I64, P, I64, P, P, P, P, I64, I32, P]),
+    "gcs_spmm_tile_capacity": (c_int32, [I64, I32]),
+    "gcs_spmm_build_tiles": (c_int32, [P, I32, I64, P, I32, P, P]),
+    "gcs_spmm_sum": (c_int32, [P, P, P, P, I64, P, I64, P, P, P, P, I64, I32, P]),
     "gcs_segment_sum_fwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_segment_sum_bwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_softmax_xent": (c_int32, [P, P, I32, I32, P, P, P, F32, P]),
@@ -70,6 +73,7 @@ PROTOTYPES = {
 }
 # test/sweep hook, not part of the header
 _DEBUG = {"gcs_debug_set_spmm_mode": (None, [I32]),
+          "gcs_debug_set_param": (None, [I32, I32]),
           "gcs_debug_launch_count": (ctypes.c_longlong, []),
           "gcs_debug_profile_begin": (None, []),
           "gcs_debug_profile_end": (c_int32, [ctypes.c_char_p, c_int32])}

@@ -121,6 +121,7 @@ class SparseAdjacency:
         self._indices = indices
         self._symmetric = symmetric
         self._t = None
+        self._tiles = None
 
     @classmethod
     def from_indices(cls, indices, dense_shape, values=None):
@@ -164,6 +165,14 @@ class SparseAdjacency:
         if self._symmetric is None:
             self._symmetric = ops.csr_is_symmetric(self.rowptr, self.colidx)
         return self._symmetric
+
+    @property
+    def tiles(self):
+        """(tile_ptr, n_tiles) graph-aligned row tiles for the aggregation kernel, or None when
+        the batch structure (graph_ptr) is unknown (uniform tiles are used then)."""
+        if self._tiles is None and self.graph_ptr is not None:
+            self._tiles = ops.build_tiles(self.graph_ptr, self.n_rows)
+        return self._tiles
 
     def transposed(self):
         """(rowptr_t, colidx_t) of pattern(A)^T; the same arrays when symmetric."""

@@ -211,10 +211,11 @@ class GeneralGNN:
         elif a.graph_ptr is not None:
             graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
         rp_t, ci_t = a.transposed() if need_transpose else (None, None)
-        batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, a.max_graph_nodes if a.graph_ptr is not None else 0,
-                           ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t), ptr(graph_ptr), ptr(x),
-                           x.stride(0) if x.shape[0] > 1 else x.shape[1], None)
-        keep = (x, a, graph_ptr, rp_t, ci_t)               # keep device buffers alive
+        tiles = a.tiles
+        tp, nt = tiles if tiles is not None else (None, None)
+        batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, 0, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
+                           ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None, ptr(tp), ptr(nt))
+        keep = (x, a, graph_ptr, rp_t, ci_t, tiles)        # keep device buffers alive
         return batch, keep
 
     def _workspace(self, batch, training):

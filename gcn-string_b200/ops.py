@@ -236,9 +236,22 @@ def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3):
 
 
 # ------------------------------------------------------------------ aggregation (K3/K7)
-def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, graph_ptr=None,
-             max_graph_rows: int = 0):
-    """Y = pattern(A) . prelu(x*scale + shift, alpha)  (identity prologue when scale is None)."""
+def build_tiles(graph_ptr, n_rows: int):
+    """Graph-aligned row tiles for the aggregation kernel -> (tile_ptr int32, n_tiles int32[1])."""
+    torch = _t()
+    lib = _lib.load()
+    b = graph_ptr.shape[0] - 1
+    cap = lib.gcs_spmm_tile_capacity(n_rows, b)
+    tile_ptr = torch.empty(cap + 1, dtype=torch.int32, device="cuda")
+    n_tiles = torch.empty(1, dtype=torch.int32, device="cuda")
+    check(lib.gcs_spmm_build_tiles(ptr(graph_ptr), b, n_rows, ptr(tile_ptr), cap, ptr(n_tiles), stream_ptr()),
+          "gcs_spmm_build_tiles")
+    return tile_ptr, n_tiles
+
+
+def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, tiles=None):
+    """Y = pattern(A) . prelu(x*scale + shift, alpha)  (identity prologue when scale is None).
+    ``tiles`` = (tile_ptr, n_tiles) from ``build_tiles`` or None for uniform row tiles."""
     torch = _t()
     lib = _lib.load()
     x, ldx = _mat(x, "x")
@@ -248,9 +261,9 @@ def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, gr
     if out is None:
         out = torch.empty(n, hdim, dtype=torch.float32, device="cuda")
     out, ldy = _mat(out, "y")
-    n_graphs = graph_ptr.shape[0] - 1 if graph_ptr is not None else 0
-    check(lib.gcs_spmm_sum(ptr(rowptr), ptr(colidx), ptr(graph_ptr), n_graphs, max_graph_rows, n, ptr(x), ldx,
-                           ptr(scale), ptr(shift), ptr(alpha), ptr(out), ldy, hdim, stream_ptr()), "gcs_spmm_sum")
+    tp, nt = tiles if tiles is not None else (None, None)
+    check(lib.gcs_spmm_sum(ptr(rowptr), ptr(colidx), ptr(tp), ptr(nt), n, ptr(x), ldx, ptr(scale), ptr(shift),
+                           ptr(alpha), ptr(out), ldy, hdim, stream_ptr()), "gcs_spmm_sum")
     return out
 
 

@@ -131,14 +131,19 @@ int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh,
  * BatchNorm+PReLU prologue of GeneralConv.call, f(x) = prelu(x*scale + shift, alpha);
  * pass scale = shift = alpha = NULL for f = identity (that is also the backward:
  * dX = pattern(A)^T . dY, called with the transposed CSR).  Neighbours are accumulated in
- * ascending column order per output row.  graph_ptr (may be NULL) enables the
- * shared-memory-staged per-graph kernel (rows of one graph only reference rows of the same
- * graph - the block-diagonal structure of a disjoint batch); max_graph_rows is the largest
- * graph of the batch if the host knows it, 0 if not.  With graph_ptr == NULL the
- * row-parallel kernel is used and the matrix may have any structure.
+ * ascending column order per output row.
+ * Row tiles: the kernel stages one tile of rows (<= 512) in shared memory per CTA.  With
+ * tile_ptr == NULL tiles are uniform; gcs_spmm_build_tiles derives graph-aligned tiles
+ * from graph_ptr (whole graphs packed per tile, larger graphs split), which keeps nearly
+ * every neighbour of a tile row inside the tile for disjoint batches.  tile_ptr needs
+ * gcs_spmm_tile_capacity(n_rows, n_graphs) + 1 int32 entries; *n_tiles_dev is written on
+ * the device.  Any matrix structure is accepted either way.
  * --------------------------------------------------------------------------------- */
-int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* graph_ptr,
-                 int32_t n_graphs, int32_t max_graph_rows, int64_t n_rows, const float* X, int64_t ldx,
+int32_t gcs_spmm_tile_capacity(int64_t n_rows, int32_t n_graphs);
+int gcs_spmm_build_tiles(const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t* tile_ptr,
+                         int32_t tile_capacity, int32_t* n_tiles_dev, gcs_stream stream);
+int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* tile_ptr,
+                 const int32_t* n_tiles_dev, int64_t n_rows, const float* X, int64_t ldx,
                  const float* scale, const float* shift, const float* alpha, float* Y, int64_t ldy,
                  int32_t H, gcs_stream stream);
 
@@ -191,7 +196,7 @@ typedef struct gcs_batch {
   int64_t n_nodes;
   int64_t nnz;
   int32_t n_graphs;
-  int32_t max_graph_nodes;  /* largest graph of the batch, 0 = unknown */
+  int32_t reserved;
   const int32_t* rowptr;    /* [N+1]  CSR of pattern(A): row = target, col = source */
   const int32_t* colidx;    /* [nnz] */
   const int32_t* rowptr_t;  /* CSR of pattern(A)^T; may equal rowptr/colidx if symmetric; */
@@ -200,6 +205,8 @@ typedef struct gcs_batch {
   const float* x;           /* [N, F] */
   int64_t ldx;
   const float* y;           /* [B, C] one-hot; NULL for inference */
+  const int32_t* tile_ptr;    /* row tiles for the aggregation kernels (gcs_spmm_build_tiles), or NULL */
+  const int32_t* n_tiles_dev; /* device scalar written by gcs_spmm_build_tiles, or NULL */
 } gcs_batch;
 
 /* Number of floats in the flat trainable / state buffers (layout: gcn-string_b200/params.py). */

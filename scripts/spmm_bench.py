@@ -31,12 +31,12 @@ def make_batch(n_graphs, n_mean, deg, seed=0):
 
 def run(a, H, mode, iters, transform=True, flush=None):
     lib = _lib.load()
-    lib.gcs_debug_set_spmm_mode({"auto": 0, "rows": 1, "staged": 2}[mode])
+    lib.gcs_debug_set_spmm_mode({"auto": 0, "rows": 1, "tile": 2, "tile_uniform": 2}[mode])
     n = a.n_rows
     x = torch.randn(n, H, device="cuda")
     y = torch.empty(n, H, device="cuda")
     sc, sh, al = (torch.rand(H, device="cuda") + 0.5, torch.randn(H, device="cuda"), torch.rand(H, device="cuda") * 0.3)
-    kw = dict(graph_ptr=a.graph_ptr, max_graph_rows=a.max_graph_nodes) if mode != "rows" else {}
+    kw = dict(tiles=a.tiles) if mode == "tile" else {}
     args = (sc, sh, al) if transform else (None, None, None)
     for _ in range(3):
         ops.spmm_sum(a.rowptr, a.colidx, x, *args, out=y, **kw)
@@ -67,17 +67,20 @@ if __name__ == "__main__":
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--sweep", action="store_true", help="BASELINE cfg4: H 16..512 x deg 4..64")
+    ap.add_argument("--param", type=int, nargs=2, action="append", default=[], help="debug knob: id value")
     args = ap.parse_args()
+    for pid, val in args.param:
+        _lib.load().gcs_debug_set_param(pid, val)
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
     if args.sweep:
         for deg in (4, 8, 16, 32, 64):
             a = make_batch(args.graphs, args.n_mean, deg)
             for H in (16, 32, 64, 128, 256, 512):
-                for mode in ("rows", "staged"):
-                    if mode == "staged" and H % 32:
+                for mode in ("rows", "tile"):
+                    if mode == "tile" and H % 32:
                         continue
                     print(json.dumps(run(a, H, mode, args.iters, flush=flush)), flush=True)
     else:
         a = make_batch(args.graphs, args.n_mean, args.deg)
-        for mode in ([args.mode] if args.mode != "auto" else ["rows", "staged"]):
+        for mode in ([args.mode] if args.mode != "auto" else ["rows", "tile", "tile_uniform"]):
             print(json.dumps(run(a, args.hidden, mode, args.iters, flush=flush)), flush=True)

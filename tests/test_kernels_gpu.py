@@ -216,7 +216,7 @@ def test_spmm_row_kernel(H, transform):
 
 
 @pytest.mark.parametrize("n_mean,H", [(60, 32), (300, 64), (700, 256), (1400, 32)])
-def test_spmm_staged_kernel_matches_row_kernel_bitwise(n_mean, H):
+def test_spmm_tile_kernel_matches_row_kernel_bitwise(n_mean, H):
     """Both kernels add neighbours in ascending column order with one owner per element, so
     they must agree bit for bit; the staged one is also checked against the oracle."""
     lib = _lib.load()
@@ -230,15 +230,22 @@ def test_spmm_staged_kernel_matches_row_kernel_bitwise(n_mean, H):
                   rng.uniform(0.1, 0.4, H).astype(np.float32))
     wide = torch.zeros(n, 3 * H, device="cuda")           # write into a slice: ldy != H
     try:
+        lib.gcs_debug_set_spmm_mode(1)
+        y_rows = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al))
         lib.gcs_debug_set_spmm_mode(2)
-        for mx in (a.max_graph_nodes, 0):                  # with and without the host's size hint
+        for tiles in (a.tiles, None):                      # graph-aligned and uniform row tiles
             y_staged = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al), out=wide[:, H:2 * H],
-                                    graph_ptr=a.graph_ptr, max_graph_rows=mx).clone()
-            lib.gcs_debug_set_spmm_mode(1)
-            y_rows = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al))
-            lib.gcs_debug_set_spmm_mode(2)
+                                    tiles=tiles).clone()
             assert np.array_equal(host(y_staged), host(y_rows))
-        y_id = ops.spmm_sum(a.rowptr, a.colidx, dev(x), graph_ptr=a.graph_ptr, max_graph_rows=a.max_graph_nodes)
+        y_id = ops.spmm_sum(a.rowptr, a.colidx, dev(x), tiles=a.tiles)
+        # the tiles partition the rows, follow graph boundaries and respect the tile size
+        tp, nt = a.tiles
+        tp = host(tp)[: int(nt.item()) + 1]
+        gp = host(a.graph_ptr)
+        assert tp[0] == 0 and tp[-1] == n and np.all(np.diff(tp) > 0) and np.diff(tp).max() <= 512
+        small = np.diff(gp) <= 512
+        inner = np.setdiff1d(tp, gp)                       # tile cuts that are not graph boundaries
+        assert all(np.searchsorted(gp, c, side="right") - 1 in np.nonzero(~small)[0] for c in inner)
     finally:
         lib.gcs_debug_set_spmm_mode(0)
     z = x.astype(np.float64) * sc + sh
@@ -246,6 +253,29 @@ def test_spmm_staged_kernel_matches_row_kernel_bitwise(n_mean, H):
     assert rel_err(host(y_staged), csr @ np.where(z > 0, z, al * z)) < TOL
     assert rel_err(host(y_id), csr @ x.astype(np.float64)) < TOL
     assert float(wide[:, :H].abs().max()) == 0.0 and float(wide[:, 2 * H:].abs().max()) == 0.0
+
+
+def test_spmm_tile_kernel_dense_rows_and_arbitrary_structure():
+    """Rows longer than the staged index buffer (4096 entries) and a non-banded random matrix:
+    the tile kernel must fall back gracefully, bit-identical to the row kernel."""
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    n = 5000
+    a = random_csr(rng, n, 0.004).tolil()
+    a[3, :] = 1                                          # one row with 5000 neighbours
+    a[300, ::2] = 1
+    a = sp.csr_matrix(a)
+    a.sort_indices()
+    x = dev(rng.standard_normal((n, 64)).astype(np.float32))
+    rp, ci = dev(a.indptr.astype(np.int32)), dev(a.indices.astype(np.int32))
+    try:
+        lib.gcs_debug_set_spmm_mode(1)
+        y_rows = ops.spmm_sum(rp, ci, x)
+        lib.gcs_debug_set_spmm_mode(2)
+        assert torch.equal(ops.spmm_sum(rp, ci, x), y_rows)
+    finally:
+        lib.gcs_debug_set_spmm_mode(0)
+    assert rel_err(host(y_rows), _spmm_ref(a, host(x))) < TOL
 
 
 def test_spmm_is_deterministic_and_handles_empty_rows():
@@ -319,5 +349,5 @@ def test_bad_arguments_raise_with_a_message():
     with pytest.raises(ValueError, match="float32"):
         ops.linear_fwd(x.double(), torch.zeros(8, 3, device="cuda"))
     lib = _lib.load()
-    st = lib.gcs_spmm_sum(None, None, None, 0, 0, 5, None, 8, None, None, None, None, 8, 8, _lib.stream_ptr())
+    st = lib.gcs_spmm_sum(None, None, None, None, 5, None, 8, None, None, None, None, 8, 8, _lib.stream_ptr())
     assert st == 1 and b"null pointer" in lib.gcs_last_error()
