@@ -46,10 +46,11 @@ PROTOTYPES = {
     "gcs_csr_is_symmetric": (c_int32, [P, P, I64, P, P]),
     "gcs_csr_transpose": (c_int32, [P, P, I64, I64, P, P, P, P]),
     "gcs_cast_f64_f32": (c_int32, [P, P, I64, P]),
-    "gcs_linear_fwd": (c_int32, [P, I64, P, P, P, I64, I64, I32, I32, P]),
+    "gcs_linear_workspace_bytes": (c_int64, [I64, I32, I32]),
+    "gcs_linear_fwd": (c_int32, [P, I64, P, P, P, I64, I64, I32, I32, P, I64, P]),
     "gcs_linear_bwd_weight_workspace_bytes": (c_int64, [I64, I32, I32]),
     "gcs_linear_bwd_weight": (c_int32, [P, I64, P, I64, P, P, I64, I32, I32, P, I64, P]),
-    "gcs_linear_bwd_input": (c_int32, [P, I64, P, P, I64, I64, I32, I32, I32, P]),
+    "gcs_linear_bwd_input": (c_int32, [P, I64, P, P, I64, I64, I32, I32, I32, P, I64, P]),
     "gcs_bn_workspace_bytes": (c_int64, [I64, I32]),
     "gcs_bn_stats": (c_int32, [P, I64, I64, I32, P, P, P, I64, P]),
     "gcs_bn_fold": (c_int32, [P, P, P, P, F32, F32, P, P, P, P, I32, P]),
@@ -74,6 +75,7 @@ PROTOTYPES = {
 # test/sweep hook, not part of the header
 _DEBUG = {"gcs_debug_set_spmm_mode": (None, [I32]),
           "gcs_debug_set_param": (None, [I32, I32]),
+          "gcs_debug_set_gemm_mode": (None, [I32]),
           "gcs_debug_launch_count": (ctypes.c_longlong, []),
           "gcs_debug_profile_begin": (None, []),
           "gcs_debug_profile_end": (c_int32, [ctypes.c_char_p, c_int32])}

@@ -238,7 +238,40 @@ static WeightSplit weight_split(int64_t M, int K, int N) {
 
 }  // namespace gcs
 
+namespace gcs {
+namespace tc {   // linear_tc.cu
+bool shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* C, int64_t ldc, const float* bias);
+int64_t split_workspace_bytes(int K, int N);
+int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
+           int64_t M, int K, int N, int accumulate, cudaStream_t st);
+int split(const float* W, int rows, int cols, bool transpose, float* hi, float* lo, cudaStream_t st);
+}  // namespace tc
+}  // namespace gcs
+
 using namespace gcs;
+
+static int g_gemm_mode = 0;   // 0 = auto (tensor cores when the shape allows), 1 = CUDA cores only, 2 = tensor cores or error
+extern "C" void gcs_debug_set_gemm_mode(int mode) { g_gemm_mode = mode; }
+
+// Tensor-core path if the shape, alignment and workspace allow it.  *used = 1 when it ran.
+static int try_tensor_cores(const float* A, int64_t lda, const float* W, int w_rows, int w_cols, bool transpose_w,
+                            const float* bias, float* C, int64_t ldc, int64_t M, int Kred, int Nout, int accumulate,
+                            void* workspace, int64_t workspace_bytes, cudaStream_t st, int* used) {
+  *used = 0;
+  if (g_gemm_mode == 1) return GCS_OK;
+  const bool ok = tc::shape_ok(M, Kred, Nout, A, lda, C, ldc, bias) && workspace && aligned16(workspace) &&
+                  workspace_bytes >= tc::split_workspace_bytes(Kred, Nout);
+  if (!ok) {
+    if (g_gemm_mode == 2) return fail(GCS_ERR_UNSUPPORTED, "tensor-core GEMM forced but shape/workspace do not allow it");
+    return GCS_OK;
+  }
+  float* hi = static_cast<float*>(workspace);
+  float* lo = hi + static_cast<int64_t>(Kred) * Nout;
+  GCS_TRY(tc::split(W, w_rows, w_cols, transpose_w, hi, lo, st));
+  GCS_TRY(tc::launch(A, lda, hi, lo, bias, C, ldc, M, Kred, Nout, accumulate, st));
+  *used = 1;
+  return GCS_OK;
+}
 
 template <bool P_RC, bool Q_JC>
 static int launch_sgemm(const float* P, int64_t ldp, const float* Q, int64_t ldq, float* C, int64_t ldc,
@@ -255,21 +288,42 @@ static int launch_sgemm(const float* P, int64_t ldp, const float* Q, int64_t ldq
   return GCS_OK;
 }
 
+extern "C" int64_t gcs_linear_workspace_bytes(int64_t M, int32_t K, int32_t N) {
+  (void)M;
+  if (K <= 0 || N <= 0) return 0;
+  return tc::split_workspace_bytes(K, N);
+}
+
 extern "C" int gcs_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C,
-                              int64_t ldc, int64_t M, int32_t K, int32_t N, gcs_stream stream) {
+                              int64_t ldc, int64_t M, int32_t K, int32_t N, void* workspace,
+                              int64_t workspace_bytes, gcs_stream stream) {
   GCS_CHECK_ARG(M >= 0 && K > 0 && N > 0, "gcs_linear_fwd: bad size M=%lld K=%d N=%d", (long long)M, K, N);
   if (M == 0) return GCS_OK;
   GCS_CHECK_ARG(A && W && C && lda >= K && ldc >= N, "gcs_linear_fwd: bad pointer / leading dimension");
+  {
+    // W [K, N] -> split + transposed to [N][K] (reduction contiguous) for the B operand
+    int used = 0;
+    GCS_TRY(try_tensor_cores(A, lda, W, K, N, true, bias, C, ldc, M, K, N, 0, workspace, workspace_bytes, as_stream(stream), &used));
+    if (used) return GCS_OK;
+  }
   const bool vec = K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(W) &&
                    aligned16(C) && (!bias || aligned16(bias));
   return launch_sgemm<true, true>(A, lda, W, N, C, ldc, bias, M, N, K, 1, K, 0, 0, vec, as_stream(stream), "gcs_linear_fwd");
 }
 
 extern "C" int gcs_linear_bwd_input(const float* dH, int64_t ldh, const float* W, float* dA, int64_t lda,
-                                    int64_t M, int32_t K, int32_t N, int32_t accumulate, gcs_stream stream) {
+                                    int64_t M, int32_t K, int32_t N, int32_t accumulate, void* workspace,
+                                    int64_t workspace_bytes, gcs_stream stream) {
   GCS_CHECK_ARG(M >= 0 && K > 0 && N > 0, "gcs_linear_bwd_input: bad size");
   if (M == 0) return GCS_OK;
   GCS_CHECK_ARG(dH && W && dA && ldh >= N && lda >= K, "gcs_linear_bwd_input: bad pointer / leading dimension");
+  {
+    // dA[m, k] = sum_n dH[m, n] W[k, n]: W as stored IS the [out][reduction] layout, no transpose
+    int used = 0;
+    GCS_TRY(try_tensor_cores(dH, ldh, W, K, N, false, nullptr, dA, lda, M, N, K, accumulate ? 1 : 0, workspace,
+                             workspace_bytes, as_stream(stream), &used));
+    if (used) return GCS_OK;
+  }
   const bool vec = K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldh % 4 == 0 && aligned16(dH) && aligned16(W) && aligned16(dA);
   // C[i=m, j=k] = sum_{r=n} dH[m, n] * W[k, n]
   return launch_sgemm<true, false>(dH, ldh, W, N, dA, lda, nullptr, M, K, N, 1, N, accumulate, 0, vec, as_stream(stream), "gcs_linear_bwd_input");

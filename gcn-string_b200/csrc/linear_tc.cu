@@ -1,0 +1,371 @@
+// K1 / K9 on the 5th-generation tensor cores: fp32-accurate dense transforms for widths that
+// are multiples of 256, as 3xTF32 error-compensated products issued with tcgen05.mma.
+//
+//   C[M, N] (+)= A[M, K] . B[K, N] (+ bias)        A: activations (fp32, any leading dim)
+//                                                   B: weights, pre-split once per call
+// fp32 parity (BASELINE.json: 1e-5 relative) rules out a single TF32/BF16 pass (~1e-3).  Each
+// operand is split a = a_hi + a_lo with a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi), and
+//   A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      (the dropped A_lo.B_lo term is ~2^-22)
+// accumulates in fp32 in tensor memory: three kind::tf32 MMAs per K step.
+//
+// The tensor core adds each K=8 step into the fp32 accumulator with truncation, a bias that grows
+// with the number of steps on a LARGE accumulator (measured 6.6e-6 at K=1024 with one chain).
+// So the main term A_hi.B_hi and the two 2^-11-smaller correction terms accumulate in SEPARATE
+// tensor-memory accumulators and meet in a single fp32 add in the epilogue.
+//
+// One CTA = one 128 x 128 output tile, 192 threads, warp-specialised:
+//   warp 0      TMA producer: raw fp32 A tile [128 x 32] and the two pre-split weight tiles
+//               [128 x 32] (K-major, 128 B rows, SWIZZLE_128B) per stage, 4 stages
+//   warp 1      MMA issuer (one elected thread): per stage 4 K-steps x 3 tcgen05.mma with the
+//               A operand in TENSOR MEMORY and B from shared memory; owns TMEM alloc/free
+//   warps 2-5   converters: each thread owns one row of the A tile, reads its 128 B from the
+//               swizzled shared tile (conflict-free), splits hi/lo in registers and writes
+//               both halves into TMEM (tcgen05.st) - the split never touches shared memory,
+//               which the B operand already keeps busy; afterwards the same warps run the
+//               epilogue (tcgen05.ld -> + bias / + C -> 128 B-per-thread row stores)
+// TMEM: columns [0, 128) main accumulator, [128, 256) correction accumulator, [256, 384) two A
+// stages of (32 hi + 32 lo) columns.  The two CTAs that share a row block (N = 256) are adjacent
+// in launch order, so the second read of the A tile is an L2 hit.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gcs {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int kStages = 4;    // shared-memory stages (TMA)
+constexpr int kAStages = 2;   // tensor-memory stages of the split A operand
+constexpr int kThreads = 192;
+constexpr uint32_t A_RAW_BYTES = BM * BK * 4;          // 16 KB
+constexpr uint32_t B_BYTES = BN * BK * 4;              // 16 KB per half
+constexpr uint32_t STAGE_BYTES = A_RAW_BYTES + 2 * B_BYTES;
+constexpr uint32_t kSmemBytes = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t ACC_MAIN = 0, ACC_CORR = 128, A_COL = 256, kTmemCols = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc], kind::tf32
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+#define GCS_R32(v) v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], \
+                   v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 128 B rows: 8-row atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);         // start address, 16 B units
+  d |= static_cast<uint64_t>(0) << 16;                            // leading byte offset (unused: one atom along K)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // stride byte offset between 8-row atoms
+  d |= static_cast<uint64_t>(1) << 46;                            // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = BM.
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                (static_cast<uint32_t>(BM >> 4) << 24);
+
+__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
+    const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+    const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C, int64_t ldc,
+    const float* __restrict__ bias, int64_t M, int K, int accumulate) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t bars = base + kStages * STAGE_BYTES;
+  // barriers (8 B each): full[4] | smem_empty[4] | a_ready[2] | a_empty[2] | acc_full | tmem ptr
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto smem_empty = [&](int s) { return bars + 32u + 8u * s; };
+  auto a_ready = [&](int t) { return bars + 64u + 8u * t; };
+  auto a_empty = [&](int t) { return bars + 80u + 8u * t; };
+  const uint32_t acc_full = bars + 96u;
+  const uint32_t tmem_slot = bars + 104u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;     // the N tiles of one row block are adjacent in launch order
+  const int m0 = blockIdx.y * BM;
+  const int num_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(smem_empty(s), 1 + 4);      // one tcgen05.commit + one arrive per converter warp
+    }
+    for (int t = 0; t < kAStages; ++t) {
+      mbar_init(a_ready(t), 128);
+      mbar_init(a_empty(t), 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(smem_empty(s), ((kb / kStages) & 1) ^ 1);
+        const uint32_t a_raw = base + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(full(s), STAGE_BYTES);
+        tma_load_2d(a_raw, &map_a, kb * BK, m0, full(s));
+        tma_load_2d(a_raw + A_RAW_BYTES, &map_b_hi, kb * BK, n0, full(s));
+        tma_load_2d(a_raw + A_RAW_BYTES + B_BYTES, &map_b_lo, kb * BK, n0, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages, t = kb % kAStages;
+        mbar_wait(full(s), (kb / kStages) & 1);        // weight tiles landed
+        mbar_wait(a_ready(t), (kb / kAStages) & 1);    // converters filled this TMEM A stage
+        tc_fence_after();
+        const uint32_t b_hi = base + s * STAGE_BYTES + A_RAW_BYTES;
+        const uint64_t d_hi = make_kmajor_sw128_desc(b_hi);
+        const uint64_t d_lo = make_kmajor_sw128_desc(b_hi + B_BYTES);
+        const uint32_t a_hi = tmem_base + A_COL + t * 64;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          // K advance inside the 128 B swizzle atom: +32 B on the start address, +8 TMEM columns
+          const uint64_t koff = static_cast<uint64_t>((k * 32) >> 4);
+          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kInstrDesc, acc);        // A_hi . B_hi
+          mma_tf32_ts(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kInstrDesc, acc);        // A_hi . B_lo
+          mma_tf32_ts(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kInstrDesc, 1u);    // A_lo . B_hi
+        }
+        tc_commit(smem_empty(s));           // weight tiles of this stage consumed
+        tc_commit(a_empty(t));              // TMEM A stage consumed
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------ converters, then epilogue
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;                 // row of the tile owned by this thread
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages, t = kb % kAStages;
+      mbar_wait(full(s), (kb / kStages) & 1);
+      const uint32_t row_addr = base + s * STAGE_BYTES + r * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 v;
+        const uint32_t addr = row_addr + ((c ^ (r & 7)) << 4);          // undo the 128 B TMA swizzle
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t h = rna_tf32(e[i]);
+          hi[4 * c + i] = h;
+          lo[4 * c + i] = rna_tf32(e[i] - __uint_as_float(h));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_empty(s));       // raw A tile consumed by this warp
+      mbar_wait(a_empty(t), ((kb / kAStages) & 1) ^ 1);   // MMAs of the previous use of this TMEM stage are done
+      tc_fence_after();
+      const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64;
+      tmem_st32(a_hi, hi);
+      tmem_st32(a_hi + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(a_ready(t));
+    }
+    // epilogue: 4 chunks of 32 columns per thread-row, main + correction accumulators
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int64_t row = static_cast<int64_t>(m0) + r;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32], w[32];
+      tmem_ld32(tmem_base + lane_addr + ACC_MAIN + c0, v);
+      tmem_ld32(tmem_base + lane_addr + ACC_CORR + c0, w);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+        float* cp = C + row * ldc + n0 + c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(w[4 * q]),
+                                 __uint_as_float(v[4 * q + 1]) + __uint_as_float(w[4 * q + 1]),
+                                 __uint_as_float(v[4 * q + 2]) + __uint_as_float(w[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]) + __uint_as_float(w[4 * q + 3]));
+          if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(cp + 4 * q);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *reinterpret_cast<float4*>(cp + 4 * q) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// hi = rna_tf32(w), lo = rna_tf32(w - hi); optionally transposed so that the reduction index
+// is contiguous (the K-major layout the B operand wants).
+__global__ void __launch_bounds__(256) split_weights_kernel(const float* __restrict__ W, int rows, int cols,
+                                                            int transpose, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<int64_t>(r) * cols);
+    const float w = __ldg(W + i);
+    const float h = __uint_as_float(rna_tf32(w));
+    const float l = __uint_as_float(rna_tf32(w - h));
+    const int64_t o = transpose ? static_cast<int64_t>(c) * rows + r : i;
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, inner] with a row pitch of ld elements; box = [box_rows, 32], SWIZZLE_128B.
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t inner, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return GCS_OK;
+}
+
+bool shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* C, int64_t ldc, const float* bias) {
+  return M > 0 && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(C) &&
+         (!bias || aligned16(bias)) && ceil_div(M, BM) <= 65535;
+}
+
+int64_t split_workspace_bytes(int K, int N) { return round_up(2LL * K * N * sizeof(float), 256); }
+
+// Bt: weights already split, laid out [N][K] (reduction contiguous): hi at Bt, lo at Bt + N*K.
+int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
+           int64_t M, int K, int N, int accumulate, cudaStream_t st) {
+  alignas(64) CUtensorMap ma, mh, ml;
+  GCS_TRY(make_map(&ma, A, M, K, lda, BM));
+  GCS_TRY(make_map(&mh, Bt_hi, N, K, K, BN));
+  GCS_TRY(make_map(&ml, Bt_lo, N, K, K, BN));
+  static bool attr = false;
+  if (!attr) {
+    GCS_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr = true;
+  }
+  dim3 grid(N / BN, static_cast<unsigned>(ceil_div(M, BM)));
+  linear_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ma, mh, ml, C, ldc, bias, M, K, accumulate);
+  GCS_CHECK_LAUNCH("linear_tc_kernel");
+  return GCS_OK;
+}
+
+int split(const float* W, int rows, int cols, bool transpose, float* hi, float* lo, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+  split_weights_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(W, rows, cols, transpose ? 1 : 0, hi, lo);
+  GCS_CHECK_LAUNCH("split_weights_kernel");
+  return GCS_OK;
+}
+
+}  // namespace tc
+}  // namespace gcs

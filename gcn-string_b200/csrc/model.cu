@@ -105,6 +105,8 @@ struct Plan {
   float* logits = nullptr;      // [rows_post, C]
   void* bn_ws = nullptr;
   int64_t bn_ws_bytes = 0;
+  void* lin_ws = nullptr;       // split weights of the tensor-core GEMM in flight
+  int64_t lin_ws_bytes = 0;
   // backward
   float* gcat = nullptr;        // [N, Wc]
   float* tmp_a = nullptr;       // [N, H]
@@ -157,6 +159,13 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
   }
   p.bn_ws_bytes = bn_bytes;
   p.bn_ws = a.take<char>(bn_bytes);
+  int64_t lin_bytes = 0;
+  for (const auto& b : p.blocks) {
+    const int64_t v = gcs_linear_workspace_bytes(N, b.k_in, b.m_out);
+    if (v > lin_bytes) lin_bytes = v;
+  }
+  p.lin_ws_bytes = lin_bytes;
+  p.lin_ws = a.take<char>(lin_bytes);
   if (training) {
     p.gcat = a.take<float>(N * p.Wc);
     p.tmp_a = a.take<float>(NH);
@@ -223,7 +232,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
   int64_t ld_in = bt.ldx;
   for (int j = 0; j < P; ++j) {
     const BlockDesc& b = p.blocks[j];
-    GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, st));
+    GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
     float* out = j < P - 1 ? p.act[j] : p.cat + static_cast<int64_t>(L) * H;
     const int64_t ld_out = j < P - 1 ? H : Wc;
@@ -237,7 +246,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     const int bi = P + k;
     const BlockDesc& b = p.blocks[bi];
     const float* cin = p.cat + static_cast<int64_t>(L - k) * H;          // trailing (k+1)*H columns
-    GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, st));
+    GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
     const float* scale = p.stat[bi] + 2 * H;
     GCS_TIMED("spmm_fwd", gcs_spmm_sum(bt.rowptr, bt.colidx, bt.tile_ptr, bt.n_tiles_dev, N,
@@ -257,7 +266,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     const int bi = P + L + j;
     const BlockDesc& b = p.blocks[bi];
     GCS_TRY(gcs_linear_fwd(pin, ld_pin, params + b.kernel(), params + b.bias(), p.post_h[j], b.m_out, R, b.k_in,
-                           b.m_out, st));
+                           b.m_out, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.post_h[j], b.m_out, R, training, st));
     const float* scale = p.stat[bi] + 2 * b.m_out;
     if (j < p.Q - 1) {
@@ -290,7 +299,7 @@ static int block_backward(const gcs_model_config& c, const Plan& p, int bi, cons
                                                        b.k_in, b.m_out, p.lw_ws, p.lw_ws_bytes, st));
   if (din)
     GCS_TIMED("linear_bwd_input", gcs_linear_bwd_input(dh, lddh, params + b.kernel(), din, lddin, rows, b.k_in,
-                                                       b.m_out, accumulate, st));
+                                                       b.m_out, accumulate, p.lin_ws, p.lin_ws_bytes, st));
   return GCS_OK;
 }
 

@@ -139,7 +139,9 @@ def linear_fwd(a, w, bias=None, out=None):
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32, device="cuda")
     out, ldc = _mat(out, "C")
-    check(lib.gcs_linear_fwd(ptr(a), lda, ptr(w), ptr(bias), ptr(out), ldc, m, k, n, stream_ptr()), "gcs_linear_fwd")
+    ws = _ws(lib.gcs_linear_workspace_bytes(m, k, n))
+    check(lib.gcs_linear_fwd(ptr(a), lda, ptr(w), ptr(bias), ptr(out), ldc, m, k, n, ptr(ws), ws.numel(), stream_ptr()),
+          "gcs_linear_fwd")
     return out
 
 
@@ -176,8 +178,9 @@ def linear_bwd_input(dh, w, out=None, accumulate=False):
             raise ValueError("accumulate=True needs an existing output")
         out = torch.empty(m, k, dtype=torch.float32, device="cuda")
     out, lda = _mat(out, "dA")
-    check(lib.gcs_linear_bwd_input(ptr(dh), ldh, ptr(w), ptr(out), lda, m, k, n, int(accumulate), stream_ptr()),
-          "gcs_linear_bwd_input")
+    ws = _ws(lib.gcs_linear_workspace_bytes(m, n, k))
+    check(lib.gcs_linear_bwd_input(ptr(dh), ldh, ptr(w), ptr(out), lda, m, k, n, int(accumulate), ptr(ws), ws.numel(),
+                                   stream_ptr()), "gcs_linear_bwd_input")
     return out
 
 

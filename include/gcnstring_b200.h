@@ -89,15 +89,22 @@ int gcs_cast_f64_f32(const double* src, float* dst, int64_t n, gcs_stream stream
  *   bwd_weight: dW[K,N] = A[M,K]^T . dH[M,N];  db[N] = colsum(dH)   (db may be NULL)
  *               workspace: gcs_linear_bwd_weight_workspace_bytes(M,K,N)
  *   bwd_input:  dA[M,K] (+)= dH[M,N] . W[K,N]^T               (accumulate != 0 adds)
+ * fwd / bwd_input run on the tensor cores (tcgen05, 3xTF32 split, fp32-accurate) when the
+ * reduction width is a multiple of 32, the output width a multiple of 128 and a workspace
+ * of gcs_linear_workspace_bytes(M,K,N) is given (it holds the split weights); otherwise, or
+ * with workspace == NULL, on the CUDA cores (exact fp32 FFMA).
  * --------------------------------------------------------------------------------- */
+int64_t gcs_linear_workspace_bytes(int64_t M, int32_t K, int32_t N);
 int gcs_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C,
-                   int64_t ldc, int64_t M, int32_t K, int32_t N, gcs_stream stream);
+                   int64_t ldc, int64_t M, int32_t K, int32_t N, void* workspace,
+                   int64_t workspace_bytes, gcs_stream stream);
 int64_t gcs_linear_bwd_weight_workspace_bytes(int64_t M, int32_t K, int32_t N);
 int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* dH, int64_t ldh, float* dW,
                           float* db, int64_t M, int32_t K, int32_t N, void* workspace,
                           int64_t workspace_bytes, gcs_stream stream);
 int gcs_linear_bwd_input(const float* dH, int64_t ldh, const float* W, float* dA, int64_t lda,
-                         int64_t M, int32_t K, int32_t N, int32_t accumulate, gcs_stream stream);
+                         int64_t M, int32_t K, int32_t N, int32_t accumulate, void* workspace,
+                         int64_t workspace_bytes, gcs_stream stream);
 
 /* ---------------------------------------------------------------------------------
  * K2/K8  BatchNormalization(momentum, epsilon) + PReLU (Keras defaults; rank-2 input).
