@@ -245,6 +245,11 @@ int64_t split_workspace_bytes(int K, int N);
 int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
            int64_t M, int K, int N, int accumulate, cudaStream_t st);
 int split(const float* W, int rows, int cols, bool transpose, float* hi, float* lo, cudaStream_t st);
+bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* dH, int64_t ldh);
+void wgrad_split(int64_t M, int K, int N, int* splits, int* kb_per_split);
+int64_t wgrad_workspace_bytes(int64_t M, int K, int N);
+int wgrad_launch(const float* A, int64_t lda, const float* dH, int64_t ldh, float* out, int64_t M, int K, int N,
+                 int splits, int kb_per_split, cudaStream_t st);
 }  // namespace tc
 }  // namespace gcs
 
@@ -332,8 +337,12 @@ extern "C" int gcs_linear_bwd_input(const float* dH, int64_t ldh, const float* W
 extern "C" int64_t gcs_linear_bwd_weight_workspace_bytes(int64_t M, int32_t K, int32_t N) {
   if (M < 0 || K <= 0 || N <= 0) return 0;
   const WeightSplit w = weight_split(M, K, N);
-  return round_up(static_cast<int64_t>(w.splits) * K * N * sizeof(float), 256) +
-         round_up(static_cast<int64_t>(w.col_splits) * N * sizeof(double), 256);
+  int64_t part = round_up(static_cast<int64_t>(w.splits) * K * N * sizeof(float), 256);
+  if (K % 128 == 0 && N % 128 == 0) {
+    const int64_t tcb = tc::wgrad_workspace_bytes(M, K, N);
+    if (tcb > part) part = tcb;
+  }
+  return part + round_up(static_cast<int64_t>(w.col_splits) * N * sizeof(double), 256);
 }
 
 extern "C" int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* dH, int64_t ldh, float* dW,
@@ -350,8 +359,25 @@ extern "C" int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* d
   float* part = static_cast<float*>(workspace);
   const bool vec = K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldh % 4 == 0 && aligned16(A) && aligned16(dH) && aligned16(dW);
   const int64_t kn = static_cast<int64_t>(K) * N;
-  // C[i=k, j=n] = sum_{r=m} A[m, k] * dH[m, n]
-  if (w.splits == 1) {
+  const int64_t part_bytes = gcs_linear_bwd_weight_workspace_bytes(M, K, N) -
+                             round_up(static_cast<int64_t>(w.col_splits) * N * sizeof(double), 256);
+  const bool use_tc = g_gemm_mode != 1 && tc::wgrad_shape_ok(M, K, N, A, lda, dH, ldh) && aligned16(dW);
+  if (g_gemm_mode == 2 && !use_tc)
+    return fail(GCS_ERR_UNSUPPORTED, "tensor-core weight gradient forced but the shape does not allow it");
+  if (use_tc) {
+    int splits, per;
+    tc::wgrad_split(M, K, N, &splits, &per);
+    if (splits == 1) {
+      GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, dW, M, K, N, 1, per, st));
+    } else {
+      GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, part, M, K, N, splits, per, st));
+      int64_t blocks = ceil_div(kn, 256);
+      if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+      split_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(part, splits, kn, dW);
+      GCS_CHECK_LAUNCH("split_reduce_kernel");
+    }
+  } else if (w.splits == 1) {
+    // C[i=k, j=n] = sum_{r=m} A[m, k] * dH[m, n]
     GCS_TRY((launch_sgemm<false, true>(A, lda, dH, ldh, dW, N, nullptr, K, N, M, 1, w.r_per_split, 0, 0, vec, st, "gcs_linear_bwd_weight")));
   } else {
     GCS_TRY((launch_sgemm<false, true>(A, lda, dH, ldh, part, N, nullptr, K, N, M, w.splits, w.r_per_split, 0, kn, vec, st, "gcs_linear_bwd_weight")));
@@ -361,8 +387,7 @@ extern "C" int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* d
     GCS_CHECK_LAUNCH("split_reduce_kernel");
   }
   if (db) {
-    double* cws = reinterpret_cast<double*>(static_cast<char*>(workspace) +
-                                            round_up(static_cast<int64_t>(w.splits) * kn * sizeof(float), 256));
+    double* cws = reinterpret_cast<double*>(static_cast<char*>(workspace) + part_bytes);
     dim3 grid(static_cast<unsigned>(ceil_div(N, 32)), w.col_splits);
     colsum_partial_kernel<<<grid, 256, 0, st>>>(dH, ldh, M, N, w.col_rows_per_split, cws);
     GCS_CHECK_LAUNCH("colsum_partial_kernel");

@@ -298,6 +298,222 @@ __global__ void __launch_bounds__(256) split_weights_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient  dW[K_in, N] = A[M, K_in]^T . dH[M, N]  on the tensor cores.
+//
+// The reduction runs over the M rows, both operands are activations (split on the fly) and both
+// are stored with the reduction index as the SLOW dimension.  One CTA = one 128 x 128 tile of dW
+// over a range of rows, 320 threads:
+//   warp 0      TMA: per 32-row step the raw A slab [32 x 128] (no swizzle) and the raw dH slab as
+//               four [32 x 32] boxes (SWIZZLE_128B_ATOM_32B = the canonical MN-major fp32 layout)
+//   warp 1      MMA issuer: A^T from tensor memory (K-major by construction), dH from shared
+//               memory as an MN-major operand; 3 MMAs per K=8 step into main / correction
+//               accumulators; owns TMEM
+//   warps 2-5   converters: thread i gathers column i of the A slab (32 conflict-free scalar
+//               loads: the transpose is free), splits it and writes both halves into TMEM; the dH
+//               slab is split element-wise in place (hi) + a second buffer (lo), then
+//               fence.proxy.async hands it to the tensor core
+//   warps 6-9   accumulators: every 16 steps (512 rows) they fold main + correction into a
+//               running fp32 sum kept in TMEM columns [384, 512) with round-to-nearest adds, so
+//               that no truncating tensor-core chain is longer than 128 K-steps; at the end they
+//               write the CTA's partial tile.  Partials are summed in a fixed order afterwards.
+static int g_wg_chain = 16;                              // K blocks (of 32 rows) per tensor-core accumulation chain
+void set_wgrad_chain(int c) { if (c > 0) g_wg_chain = c; }
+constexpr int kWgThreads = 320;
+constexpr uint32_t WG_X_BYTES = 32 * 128 * 4;            // 16 KB raw A slab
+constexpr uint32_t WG_Y_BYTES = 32 * 128 * 4;            // 16 KB dH slab (hi in place) ; + 16 KB lo
+constexpr uint32_t WG_STAGE_BYTES = WG_X_BYTES + 2 * WG_Y_BYTES;
+constexpr uint32_t kWgSmemBytes = kStages * WG_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t RUN_COL = 384;
+// D = F32, A = B = TF32, A K-major (TMEM), B MN-major, N = 128, M = 128
+constexpr uint32_t kWgInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | (static_cast<uint32_t>(128 >> 3) << 17) |
+                                  (static_cast<uint32_t>(128 >> 4) << 24);
+
+// MN-major fp32 operand, SWIZZLE_128B_BASE32B: 128 B rows (32 elements along N), 4-row swizzle
+// groups 512 B apart along K, 32-column boxes 4096 B apart along N.
+__device__ __forceinline__ uint64_t make_mnmajor_b32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(4096 >> 4) << 16;                    // leading byte offset: next 32-column box
+  d |= static_cast<uint64_t>(512 >> 4) << 32;                     // stride byte offset: next 4-row group
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;                            // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
+    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+    float* __restrict__ out, int64_t out_split_stride, int ldo, int num_kb_total, int kb_per_split, int kWgChain) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bars = base + kStages * WG_STAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto smem_empty = [&](int s) { return bars + 32u + 8u * s; };
+  auto a_ready = [&](int t) { return bars + 64u + 8u * t; };
+  auto a_empty = [&](int t) { return bars + 80u + 8u * t; };
+  const uint32_t acc_full = bars + 96u, acc_empty = bars + 104u, tmem_slot = bars + 112u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * 128, j0 = blockIdx.y * 128;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;                 // host guarantees >= 1
+  out += static_cast<int64_t>(blockIdx.z) * out_split_stride;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y));
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(smem_empty(s), 1);
+    }
+    for (int t = 0; t < kAStages; ++t) {
+      mbar_init(a_ready(t), 128);
+      mbar_init(a_empty(t), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(smem_empty(s), ((kb / kStages) & 1) ^ 1);
+        const uint32_t xs = base + s * WG_STAGE_BYTES;
+        const int m = (kb_begin + kb) * 32;
+        mbar_arrive_expect_tx(full(s), WG_X_BYTES + WG_Y_BYTES);
+        tma_load_2d(xs, &map_x, i0, m, full(s));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(xs + WG_X_BYTES + b * 4096, &map_y, j0 + 32 * b, m, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages, t = kb % kAStages;
+        const int chain = kb / kWgChain, pos = kb % kWgChain;
+        if (pos == 0 && chain > 0) mbar_wait(acc_empty, (chain - 1) & 1);   // accumulators drained
+        mbar_wait(a_ready(t), (kb / kAStages) & 1);     // TMEM A stage and split dH slab are ready
+        tc_fence_after();
+        const uint32_t y_hi = base + s * WG_STAGE_BYTES + WG_X_BYTES;
+        const uint64_t d_hi = make_mnmajor_b32_desc(y_hi);
+        const uint64_t d_lo = make_mnmajor_b32_desc(y_hi + WG_Y_BYTES);
+        const uint32_t a_hi = tmem_base + A_COL + t * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * 8 * 128) >> 4);       // 8 rows of 128 B per K step
+          const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
+          mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kWgInstrDesc, acc);
+          mma_tf32_ts(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kWgInstrDesc, acc);
+          mma_tf32_ts(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kWgInstrDesc, 1u);
+        }
+        tc_commit(smem_empty(s));
+        tc_commit(a_empty(t));
+        if (pos == kWgChain - 1 || kb == num_kb - 1) tc_commit(acc_full);
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ converters
+    const int quarter = warp & 3;
+    const int i = quarter * 32 + lane;                 // output row (column of the A slab) owned by this thread
+    const int ct = (warp - 2) * 32 + lane;             // 0..127: share of the dH slab
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages, t = kb % kAStages;
+      mbar_wait(full(s), (kb / kStages) & 1);
+      const uint32_t xs = base + s * WG_STAGE_BYTES;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int m = 0; m < 32; ++m) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (m * 128 + i) * 4));
+        const uint32_t h = rna_tf32(v);
+        hi[m] = h;
+        lo[m] = rna_tf32(v - __uint_as_float(h));
+      }
+      mbar_wait(a_empty(t), ((kb / kAStages) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64;
+      tmem_st32(a_hi, hi);
+      tmem_st32(a_hi + 32, lo);
+      // dH slab: hi in place, lo into the second buffer (element-wise, layout-agnostic)
+      const uint32_t ys = xs + WG_X_BYTES;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t addr = ys + (ct + 128 * u) * 16;
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+        const float hx = __uint_as_float(rna_tf32(v.x)), hy = __uint_as_float(rna_tf32(v.y));
+        const float hz = __uint_as_float(rna_tf32(v.z)), hw = __uint_as_float(rna_tf32(v.w));
+        const float lx = __uint_as_float(rna_tf32(v.x - hx)), ly = __uint_as_float(rna_tf32(v.y - hy));
+        const float lz = __uint_as_float(rna_tf32(v.z - hz)), lw = __uint_as_float(rna_tf32(v.w - hw));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + WG_Y_BYTES), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the tensor core
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(a_ready(t));
+    }
+  } else {
+    // ------------------------------------------------------------ accumulators
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int num_chains = (num_kb + kWgChain - 1) / kWgChain;
+    for (int chain = 0; chain < num_chains; ++chain) {
+      mbar_wait(acc_full, chain & 1);
+      tc_fence_after();
+      const bool last = chain == num_chains - 1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32], w[32], run[32];
+        tmem_ld32(tmem_base + lane_addr + ACC_MAIN + c0, v);
+        tmem_ld32(tmem_base + lane_addr + ACC_CORR + c0, w);
+        if (chain > 0) tmem_ld32(tmem_base + lane_addr + RUN_COL + c0, run);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          float x = __uint_as_float(v[q]) + __uint_as_float(w[q]);
+          if (chain > 0) x += __uint_as_float(run[q]);
+          run[q] = __float_as_uint(x);
+        }
+        if (!last) {
+          tmem_st32(tmem_base + lane_addr + RUN_COL + c0, run);
+        } else {
+          float* op = out + static_cast<int64_t>(i0 + r) * ldo + j0 + c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(op + 4 * q) = make_float4(__uint_as_float(run[4 * q]), __uint_as_float(run[4 * q + 1]),
+                                                                 __uint_as_float(run[4 * q + 2]), __uint_as_float(run[4 * q + 3]));
+        }
+      }
+      if (!last) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -318,16 +534,17 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, inner] with a row pitch of ld elements; box = [box_rows, 32], SWIZZLE_128B.
-static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t inner, int64_t ld, int box_rows) {
+// 2-D fp32 tensor [rows, inner] with a row pitch of ld elements; box = [box_rows, box_inner].
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t inner, int64_t ld, int box_rows,
+                    int box_inner = BK, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return GCS_OK;
@@ -355,6 +572,50 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
   dim3 grid(N / BN, static_cast<unsigned>(ceil_div(M, BM)));
   linear_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ma, mh, ml, C, ldc, bias, M, K, accumulate);
   GCS_CHECK_LAUNCH("linear_tc_kernel");
+  return GCS_OK;
+}
+
+bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* dH, int64_t ldh) {
+  return M > 0 && K % 128 == 0 && N % 128 == 0 && lda % 4 == 0 && ldh % 4 == 0 && aligned16(A) && aligned16(dH) &&
+         M < (1LL << 31) - 64;
+}
+
+// Number of row splits (grid.z) and K blocks per split for the weight-gradient kernel.
+void wgrad_split(int64_t M, int K, int N, int* splits, int* kb_per_split) {
+  const int64_t tiles = static_cast<int64_t>(K / 128) * (N / 128);
+  const int64_t nkb = ceil_div(M, 32);
+  int64_t s = ceil_div(4LL * sm_count(), tiles);
+  const int kWgChain = g_wg_chain;
+  const int64_t max_s = ceil_div(nkb, kWgChain);          // at least one full chain per split
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  int64_t per = ceil_div(nkb, s);
+  per = round_up(per, kWgChain);                           // whole chains except in the last split
+  *kb_per_split = static_cast<int>(per);
+  *splits = static_cast<int>(ceil_div(nkb, per));
+}
+
+int64_t wgrad_workspace_bytes(int64_t M, int K, int N) {
+  int s, per;
+  wgrad_split(M, K, N, &s, &per);
+  return round_up(static_cast<int64_t>(s) * K * N * sizeof(float), 256);
+}
+
+// partials: [splits][K][N]; with one split the result goes straight to dW (ld = N).
+int wgrad_launch(const float* A, int64_t lda, const float* dH, int64_t ldh, float* out, int64_t M, int K, int N,
+                 int splits, int kb_per_split, cudaStream_t st) {
+  alignas(64) CUtensorMap mx, my;
+  GCS_TRY(make_map(&mx, A, M, K, lda, 32, 128, CU_TENSOR_MAP_SWIZZLE_NONE));
+  GCS_TRY(make_map(&my, dH, M, N, ldh, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  static bool attr = false;
+  if (!attr) {
+    GCS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    attr = true;
+  }
+  dim3 grid(K / 128, N / 128, splits);
+  wgrad_tc_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(mx, my, out, static_cast<int64_t>(K) * N, N,
+                                                         static_cast<int>(ceil_div(M, 32)), kb_per_split, g_wg_chain);
+  GCS_CHECK_LAUNCH("wgrad_tc_kernel");
   return GCS_OK;
 }
 

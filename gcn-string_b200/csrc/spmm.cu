@@ -392,8 +392,10 @@ int g_spmm_mode = 0;   // 0 = auto, 1 = row kernel, 2 = tile kernel
 
 // Test / sweep hook (not part of the drop-in surface).
 extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
+namespace gcs { namespace tc { void set_wgrad_chain(int c); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
+  if (id == 3) gcs::tc::set_wgrad_chain(value);
 }
 
 extern "C" int32_t gcs_spmm_tile_capacity(int64_t n_rows, int32_t n_graphs) {

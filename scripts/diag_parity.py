@@ -37,6 +37,13 @@ def run(n_graphs, n_mean, H, L, smooth, seed=0):
         print(f"   {name:22s} |ref|={np.abs(r).max():.2e} gpu {np.abs(got[off:off+n]-r).max()/den:.2e} o2 {np.abs(r2['grads'][off:off+n]-r).max()/den:.2e}")
 
 if __name__ == "__main__":
-    run(8, 500, 256, 4, False)
-    run(8, 500, 256, 4, True)
-    run(6, 50, 32, 4, True, seed=12)
+    from gcn_string_b200 import _lib
+    if len(sys.argv) > 1:
+        for c in sys.argv[1:]:
+            _lib.load().gcs_debug_set_param(3, int(c))
+            print("#### wgrad chain", c)
+            run(8, 500, 256, 4, True)
+    else:
+        run(8, 500, 256, 4, False)
+        run(8, 500, 256, 4, True)
+        run(6, 50, 32, 4, True, seed=12)

@@ -30,7 +30,32 @@ def check(M, K, N, accumulate=False, seed=0):
         got = ops.linear_bwd_input(dH, W, out=base.clone(), accumulate=True)
         lib.gcs_debug_set_gemm_mode(0)
         res["err_tc_bwd_input"] = (got.double() - ref2).abs().max().item() / ref2.abs().max().item()
+    # weight gradient
+    if K % 128 == 0:
+        ref3 = A.double().T @ dH.double()
+        r3 = {}
+        for mode, name in ((1, "ffma"), (2, "tc")):
+            lib.gcs_debug_set_gemm_mode(mode)
+            dw, db = ops.linear_bwd_weight(A, dH)
+            r3[name] = (dw.double() - ref3).abs().max().item() / ref3.abs().max().item()
+        lib.gcs_debug_set_gemm_mode(0)
+        res["err_wgrad_ffma"], res["err_wgrad_tc"] = r3["ffma"], r3["tc"]
     return res
+
+def bench_wgrad(M, K, N, iters=5):
+    A = torch.randn(M, K, device="cuda"); dH = torch.randn(M, N, device="cuda")
+    r = {"wgrad": 1, "M": M, "K": K, "N": N}
+    for mode, name in ((1, "ffma"), (2, "tc")):
+        lib.gcs_debug_set_gemm_mode(mode)
+        for _ in range(2): ops.linear_bwd_weight(A, dH)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters): ops.linear_bwd_weight(A, dH)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        r[name + "_ms"] = ms; r[name + "_tflops"] = 2.0 * M * K * N / ms / 1e9
+    lib.gcs_debug_set_gemm_mode(0)
+    return r
 
 def bench(M, K, N, iters=10):
     A = torch.randn(M, K, device="cuda"); W = torch.randn(K, N, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
@@ -49,8 +74,10 @@ def bench(M, K, N, iters=10):
     return r
 
 if __name__ == "__main__":
-    for shape in [(128, 32, 256), (300, 64, 256), (1000, 256, 256), (4096, 1024, 256), (777, 1280, 512)]:
+    for shape in [(128, 32, 256), (300, 64, 256), (1000, 256, 256), (4096, 1024, 256), (777, 1280, 512), (70001, 256, 256)]:
         print(json.dumps(check(*shape)), flush=True)
     if "--bench" in sys.argv:
         for shape in [(516776, 32, 256), (516776, 256, 256), (516776, 512, 256), (516776, 1024, 256)]:
             print(json.dumps(bench(*shape)), flush=True)
+        for shape in [(516776, 256, 256), (516776, 1024, 256)]:
+            print(json.dumps(bench_wgrad(*shape)), flush=True)
