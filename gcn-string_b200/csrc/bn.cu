@@ -221,8 +221,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(
   block_store_partials<3 * VEC>(acc, ws + (static_cast<int64_t>(blockIdx.y) * C + c) * 3, 0, 0, c < C);
 }
 
-// coef[c] = {S1/M, S2/M} as floats for the apply pass; dgamma/dbeta/dalpha written here.
+// Per column for the apply pass: coef[4c..4c+3] = {S1/M, S2/M, rstd, gamma*rstd}; dgamma/dbeta/dalpha
+// are written here.
 __global__ void bn_bwd_final_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
+                                    const float* __restrict__ var, const float* __restrict__ gamma, float eps,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     float* __restrict__ dalpha, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,23 +237,41 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ ws, int splits, i
   if (dbeta) dbeta[c] = static_cast<float>(s1);
   if (dgamma) dgamma[c] = static_cast<float>(s2);
   if (dalpha) dalpha[c] = static_cast<float>(s3);
-  coef[2 * c] = static_cast<float>(s1 / static_cast<double>(M));
-  coef[2 * c + 1] = static_cast<float>(s2 / static_cast<double>(M));
+  const float rs = __frsqrt_rn(var[c] + eps);
+  coef[4 * c] = static_cast<float>(s1 / static_cast<double>(M));
+  coef[4 * c + 1] = static_cast<float>(s2 / static_cast<double>(M));
+  coef[4 * c + 2] = rs;
+  coef[4 * c + 3] = gamma[c] * rs;
 }
 
-// Backward pass 2: dh = gamma*rstd*(dz - S1/M - xhat*S2/M).
+// Backward pass 2: dh = gamma*rstd*(dz - S1/M - xhat*S2/M).  Same thread->column mapping as the
+// reduction pass (lane = VEC columns, 8 row warps per block, grid.y row splits), so the per-column
+// coefficients stay in registers for the whole row loop.
 template <int VEC>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const float* __restrict__ da, int64_t ldda, const float* __restrict__ h, int64_t ldh,
-    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
-    const float* __restrict__ beta, const float* __restrict__ alpha, float eps,
-    const float* __restrict__ coef, float* __restrict__ dh, int64_t lddh, int64_t M, int C) {
-  const int cpr = (C + VEC - 1) / VEC;
-  const int64_t total = M * cpr;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = idx / cpr;
-    const int c = static_cast<int>(idx - r * cpr) * VEC;
+    const float* __restrict__ mean, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ alpha, const float* __restrict__ coef, float* __restrict__ dh, int64_t lddh,
+    int64_t M, int C, int64_t rows_per_split) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + lane) * VEC;
+  if (c >= C) return;
+  const int64_t rb = blockIdx.y * rows_per_split;
+  int64_t re = rb + rows_per_split;
+  if (re > M) re = M;
+  float mu[VEC], rs[VEC], ga[VEC], be[VEC], al[VEC], c1[VEC], c2[VEC], gr[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    mu[k] = __ldg(mean + c + k);
+    ga[k] = __ldg(gamma + c + k);
+    be[k] = __ldg(beta + c + k);
+    al[k] = alpha ? __ldg(alpha + c + k) : 1.f;
+    c1[k] = __ldg(coef + 4 * (c + k));
+    c2[k] = __ldg(coef + 4 * (c + k) + 1);
+    rs[k] = __ldg(coef + 4 * (c + k) + 2);
+    gr[k] = __ldg(coef + 4 * (c + k) + 3);
+  }
+  for (int64_t r = rb + warp; r < re; r += 8) {
     float hv[VEC], gv[VEC], o[VEC];
     if (VEC == 4) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
@@ -264,16 +284,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const float mu = __ldg(mean + c + k), rs = __frsqrt_rn(__ldg(var + c + k) + eps);
-      const float ga = __ldg(gamma + c + k), be = __ldg(beta + c + k);
-      const float xhat = (hv[k] - mu) * rs;
-      const float z = fmaf(ga, xhat, be);
+      const float xhat = (hv[k] - mu[k]) * rs[k];
+      const float z = fmaf(ga[k], xhat, be[k]);
       float dz = gv[k];
-      if (alpha) {
-        const float al = __ldg(alpha + c + k);
-        dz = z > 0.f ? gv[k] : (z < 0.f ? gv[k] * al : 0.f);
-      }
-      o[k] = ga * rs * (dz - __ldg(coef + 2 * (c + k)) - xhat * __ldg(coef + 2 * (c + k) + 1));
+      if (alpha) dz = z > 0.f ? gv[k] : (z < 0.f ? gv[k] * al[k] : 0.f);
+      o[k] = gr[k] * (dz - c1[k] - xhat * c2[k]);
     }
     if (VEC == 4) *reinterpret_cast<float4*>(dh + r * lddh + c) = make_float4(o[0], o[1], o[2], o[3]);
     else dh[r * lddh + c] = o[0];
@@ -293,7 +308,7 @@ static inline int64_t elementwise_blocks(int64_t work) {
 extern "C" int64_t gcs_bn_workspace_bytes(int64_t M, int32_t C) {
   if (M < 0 || C <= 0) return 0;
   return round_up(bn_max_splits(M) * C * 3 * static_cast<int64_t>(sizeof(double)), 256) +
-         round_up(2LL * C * sizeof(float), 256);
+         round_up(4LL * C * sizeof(float), 256);
 }
 
 extern "C" int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, float* mean, float* var,
@@ -363,10 +378,10 @@ extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, i
   if (vec) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
   else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
   GCS_CHECK_LAUNCH("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, M, dgamma, dbeta, dalpha, coef);
+  bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, M, var, gamma, eps, dgamma, dbeta, dalpha, coef);
   GCS_CHECK_LAUNCH("bn_bwd_final_kernel");
-  if (vec) bn_bwd_apply_kernel<4><<<static_cast<unsigned>(elementwise_blocks(M * (C / 4))), 256, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, coef, dh, lddh, M, C);
-  else bn_bwd_apply_kernel<1><<<static_cast<unsigned>(elementwise_blocks(M * C)), 256, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, coef, dh, lddh, M, C);
+  if (vec) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split);
+  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split);
   GCS_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return GCS_OK;
 }

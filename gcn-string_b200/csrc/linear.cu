@@ -180,26 +180,42 @@ __global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restri
   }
 }
 
-// db[j] = sum_m dH[m, j]: per-split column partials (fp32 within a split of <= a few
-// thousand rows, combined in fp64 in split order).
+// db[j] = sum_m dH[m, j]: per-split column partials in fp64 (lane = 4 columns when aligned, 8 row
+// warps), combined in split order.
+template <int VEC>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dH, int64_t ldh,
                                                              int64_t M, int N, int64_t rows_per_split,
                                                              double* __restrict__ ws) {
-  __shared__ double sm[8][32];
+  __shared__ double sm[8][32][VEC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+  const int c = (blockIdx.x * 32 + lane) * VEC;
   const int64_t rb = blockIdx.y * rows_per_split;
   int64_t re = rb + rows_per_split;
   if (re > M) re = M;
-  double acc = 0.0;
-  if (c < N)
-    for (int64_t r = rb + warp; r < re; r += 8) acc += static_cast<double>(__ldg(dH + r * ldh + c));
-  sm[warp][lane] = acc;
+  double acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
+  if (c < N) {
+    for (int64_t r = rb + warp; r < re; r += 8) {
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(dH + r * ldh + c));
+        acc[0] += static_cast<double>(t.x); acc[1] += static_cast<double>(t.y);
+        acc[2] += static_cast<double>(t.z); acc[3] += static_cast<double>(t.w);
+      } else {
+        acc[0] += static_cast<double>(__ldg(dH + r * ldh + c));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) sm[warp][lane][k] = acc[k];
   __syncthreads();
   if (warp == 0 && c < N) {
-    double s = sm[0][lane];
-    for (int w = 1; w < 8; ++w) s += sm[w][lane];
-    ws[static_cast<int64_t>(blockIdx.y) * N + c] = s;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      double t = sm[0][lane][k];
+      for (int w = 1; w < 8; ++w) t += sm[w][lane][k];
+      ws[static_cast<int64_t>(blockIdx.y) * N + c + k] = t;
+    }
   }
 }
 
@@ -227,7 +243,7 @@ static WeightSplit weight_split(int64_t M, int K, int N) {
   if (s < 1) s = 1;
   w.r_per_split = round_up(ceil_div(M > 0 ? M : 1, s), BR);
   w.splits = static_cast<int>(ceil_div(M > 0 ? M : 1, w.r_per_split));
-  int64_t cs = ceil_div(2LL * sm_count(), ceil_div(N, 32));
+  int64_t cs = ceil_div(4LL * sm_count(), ceil_div(N, 128));
   const int64_t max_cs = ceil_div(M > 0 ? M : 1, 64);
   if (cs > max_cs) cs = max_cs;
   if (cs < 1) cs = 1;
@@ -388,8 +404,13 @@ extern "C" int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* d
   }
   if (db) {
     double* cws = reinterpret_cast<double*>(static_cast<char*>(workspace) + part_bytes);
-    dim3 grid(static_cast<unsigned>(ceil_div(N, 32)), w.col_splits);
-    colsum_partial_kernel<<<grid, 256, 0, st>>>(dH, ldh, M, N, w.col_rows_per_split, cws);
+    if (N % 4 == 0 && ldh % 4 == 0 && aligned16(dH)) {
+      dim3 grid(static_cast<unsigned>(ceil_div(N, 128)), w.col_splits);
+      colsum_partial_kernel<4><<<grid, 256, 0, st>>>(dH, ldh, M, N, w.col_rows_per_split, cws);
+    } else {
+      dim3 grid(static_cast<unsigned>(ceil_div(N, 32)), w.col_splits);
+      colsum_partial_kernel<1><<<grid, 256, 0, st>>>(dH, ldh, M, N, w.col_rows_per_split, cws);
+    }
     GCS_CHECK_LAUNCH("colsum_partial_kernel");
     colsum_final_kernel<<<static_cast<unsigned>(ceil_div(N, 128)), 128, 0, st>>>(cws, w.col_splits, N, db);
     GCS_CHECK_LAUNCH("colsum_final_kernel");

@@ -103,6 +103,7 @@ class GeneralGNN:
         self.losses: List = []          # no regularisers (gcn.py:335 adds sum(model.losses) == 0)
         self.cfg: Optional[GNNConfig] = None
         self._ws = None
+        self.use_row_tiles = False
 
     # ------------------------------------------------------------------ build / parameters
     def build(self, in_features: int):
@@ -211,7 +212,7 @@ class GeneralGNN:
         elif a.graph_ptr is not None:
             graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
         rp_t, ci_t = a.transposed() if need_transpose else (None, None)
-        tiles = a.tiles
+        tiles = a.tiles if self.use_row_tiles else None    # only the tile SpMM (spmm mode 2) reads them
         tp, nt = tiles if tiles is not None else (None, None)
         batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, 0, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
                            ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None, ptr(tp), ptr(nt))
