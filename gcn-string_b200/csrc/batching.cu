@@ -233,15 +233,8 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
   if (t == 0) out[n] = carry;
 }
 
-// Entry (r,c) of A lands in row c of A^T at rank = #entries (r',c) with r' < r.  Rows of A
-// are visited in ascending order by ONE thread per column list being built?  No: each
-// thread handles one source row r and, for each of its entries (r,c), computes the rank by
-// counting, inside column c's CSR row of the ORIGINAL matrix when it is symmetric this is
-// a binary search; in general we count entries of column c in rows < r with a cursor
-// array instead.  Deterministic variant used here: process source rows in ascending order
-// per target row via a per-target binary search over a (row,col)-sorted key list is more
-// machinery than the structure needs, so we fill with integer cursors and then sort each
-// (short) output row; the sorted result is unique, hence deterministic.
+// Entry (r,c) of A lands in row c of A^T.  Slots are claimed with integer cursors and each (short)
+// output row is sorted afterwards: the sorted result is unique, hence deterministic.
 __global__ void tr_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                int64_t n_rows, const int32_t* __restrict__ rowptr_t,
                                int32_t* __restrict__ cursor, int32_t* __restrict__ colidx_t) {
@@ -274,6 +267,13 @@ __global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __res
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x)
     dst[k] = static_cast<float>(src[k]);   // cvt.rn.f32.f64
+}
+
+// out[0..n] = exclusive prefix sums of cnt[0..n) (out[n] = total); shared with spmm.cu.
+int exclusive_scan_i32(const int32_t* cnt, int64_t n, int32_t* out, cudaStream_t st) {
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(cnt, n, out);
+  GCS_CHECK_LAUNCH("exclusive_scan_kernel");
+  return GCS_OK;
 }
 
 }  // namespace gcs

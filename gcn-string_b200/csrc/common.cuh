@@ -18,6 +18,8 @@ inline cudaStream_t as_stream(gcs_stream s) { return reinterpret_cast<cudaStream
 // Number of SMs on the current device (cached per device).
 int sm_count();
 
+int exclusive_scan_i32(const int32_t* cnt, int64_t n, int32_t* out, cudaStream_t st);   // batching.cu
+
 // Count of kernel launches issued by this library (bench.py's `gpu_launches`).
 void count_launch();
 

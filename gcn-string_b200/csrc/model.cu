@@ -249,7 +249,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
     const float* scale = p.stat[bi] + 2 * H;
-    GCS_TIMED("spmm_fwd", gcs_spmm_sum(bt.rowptr, bt.colidx, bt.tile_ptr, bt.n_tiles_dev, N,
+    GCS_TIMED("spmm_fwd", gcs_spmm_sum(bt.rowptr, bt.colidx, bt.rb8_blk_ptr, bt.rb8_ent, N,
                                        p.h[bi], H, scale, scale + H, params + b.alpha(),
                                        p.cat + static_cast<int64_t>(L - k - 1) * H, Wc, H, st));
   }
@@ -332,7 +332,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
   for (int k = L - 1; k >= 0; --k) {
     const int bi = P + k;
     const float* dz = p.gcat + static_cast<int64_t>(L - k - 1) * H;
-    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.tile_ptr, bt.n_tiles_dev, N, dz,
+    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb8_blk_ptr_t, bt.rb8_ent_t, N, dz,
                                        Wc, nullptr, nullptr, nullptr, p.tmp_a, H, H, st));
     GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N,
                            p.cat + static_cast<int64_t>(L - k) * H, Wc, p.tmp_b, H,

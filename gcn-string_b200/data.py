@@ -121,7 +121,8 @@ class SparseAdjacency:
         self._indices = indices
         self._symmetric = symmetric
         self._t = None
-        self._tiles = None
+        self._rb8 = None
+        self._rb8_t = None
 
     @classmethod
     def from_indices(cls, indices, dense_shape, values=None):
@@ -167,12 +168,18 @@ class SparseAdjacency:
         return self._symmetric
 
     @property
-    def tiles(self):
-        """(tile_ptr, n_tiles) graph-aligned row tiles for the aggregation kernel, or None when
-        the batch structure (graph_ptr) is unknown (uniform tiles are used then)."""
-        if self._tiles is None and self.graph_ptr is not None:
-            self._tiles = ops.build_tiles(self.graph_ptr, self.n_rows)
-        return self._tiles
+    def rb8(self):
+        """(blk_ptr, ent): RB8 row-block form of the pattern for the aggregation kernel."""
+        if self._rb8 is None:
+            self._rb8 = ops.build_rb8(self.rowptr, self.colidx)
+        return self._rb8
+
+    @property
+    def rb8_t(self):
+        """RB8 form of the transposed pattern (the same arrays when symmetric)."""
+        if self._rb8_t is None:
+            self._rb8_t = self.rb8 if self.symmetric else ops.build_rb8(*self.transposed())
+        return self._rb8_t
 
     def transposed(self):
         """(rowptr_t, colidx_t) of pattern(A)^T; the same arrays when symmetric."""

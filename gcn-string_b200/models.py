@@ -103,7 +103,7 @@ class GeneralGNN:
         self.losses: List = []          # no regularisers (gcn.py:335 adds sum(model.losses) == 0)
         self.cfg: Optional[GNNConfig] = None
         self._ws = None
-        self.use_row_tiles = False
+        self.use_rb8 = True      # row-block (RB8) aggregation format, built once per batch
 
     # ------------------------------------------------------------------ build / parameters
     def build(self, in_features: int):
@@ -212,11 +212,13 @@ class GeneralGNN:
         elif a.graph_ptr is not None:
             graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
         rp_t, ci_t = a.transposed() if need_transpose else (None, None)
-        tiles = a.tiles if self.use_row_tiles else None    # only the tile SpMM (spmm mode 2) reads them
-        tp, nt = tiles if tiles is not None else (None, None)
+        use_rb8 = self.use_rb8 and x.shape[0] < (1 << 24) and self.cfg.hidden % 4 == 0
+        rb8 = a.rb8 if use_rb8 else (None, None)
+        rb8_t = (None, None)     # the prologue-free backward gather is faster on the plain CSR kernel
         batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, 0, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
-                           ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None, ptr(tp), ptr(nt))
-        keep = (x, a, graph_ptr, rp_t, ci_t, tiles)        # keep device buffers alive
+                           ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None,
+                           ptr(rb8[0]), ptr(rb8[1]), ptr(rb8_t[0]), ptr(rb8_t[1]))
+        keep = (x, a, graph_ptr, rp_t, ci_t, rb8, rb8_t)   # keep device buffers alive
         return batch, keep
 
     def _workspace(self, batch, training):

@@ -239,22 +239,23 @@ def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3):
 
 
 # ------------------------------------------------------------------ aggregation (K3/K7)
-def build_tiles(graph_ptr, n_rows: int):
-    """Graph-aligned row tiles for the aggregation kernel -> (tile_ptr int32, n_tiles int32[1])."""
+def build_rb8(rowptr, colidx):
+    """RB8 row-block format of a CSR pattern -> (blk_ptr int32 [ceil(n/8)+1], ent uint32-as-int32 [nnz])."""
     torch = _t()
     lib = _lib.load()
-    b = graph_ptr.shape[0] - 1
-    cap = lib.gcs_spmm_tile_capacity(n_rows, b)
-    tile_ptr = torch.empty(cap + 1, dtype=torch.int32, device="cuda")
-    n_tiles = torch.empty(1, dtype=torch.int32, device="cuda")
-    check(lib.gcs_spmm_build_tiles(ptr(graph_ptr), b, n_rows, ptr(tile_ptr), cap, ptr(n_tiles), stream_ptr()),
-          "gcs_spmm_build_tiles")
-    return tile_ptr, n_tiles
+    n = rowptr.shape[0] - 1
+    nnz = colidx.shape[0]
+    blk_ptr = torch.empty((n + 7) // 8 + 1, dtype=torch.int32, device="cuda")
+    ent = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
+    ws = _ws(lib.gcs_spmm_rb8_workspace_bytes(n))
+    check(lib.gcs_spmm_build_rb8(ptr(rowptr), ptr(colidx), n, nnz, ptr(blk_ptr), ptr(ent), ptr(ws), ws.numel(),
+                                 stream_ptr()), "gcs_spmm_build_rb8")
+    return blk_ptr, ent
 
 
-def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, tiles=None):
+def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, rb8=None):
     """Y = pattern(A) . prelu(x*scale + shift, alpha)  (identity prologue when scale is None).
-    ``tiles`` = (tile_ptr, n_tiles) from ``build_tiles`` or None for uniform row tiles."""
+    ``rb8`` = (blk_ptr, ent) from ``build_rb8`` selects the row-block kernel (same results)."""
     torch = _t()
     lib = _lib.load()
     x, ldx = _mat(x, "x")
@@ -264,8 +265,8 @@ def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, ti
     if out is None:
         out = torch.empty(n, hdim, dtype=torch.float32, device="cuda")
     out, ldy = _mat(out, "y")
-    tp, nt = tiles if tiles is not None else (None, None)
-    check(lib.gcs_spmm_sum(ptr(rowptr), ptr(colidx), ptr(tp), ptr(nt), n, ptr(x), ldx, ptr(scale), ptr(shift),
+    bp, en = rb8 if rb8 is not None else (None, None)
+    check(lib.gcs_spmm_sum(ptr(rowptr), ptr(colidx), ptr(bp), ptr(en), n, ptr(x), ldx, ptr(scale), ptr(shift),
                            ptr(alpha), ptr(out), ldy, hdim, stream_ptr()), "gcs_spmm_sum")
     return out
 

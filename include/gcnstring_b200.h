@@ -139,18 +139,20 @@ int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh,
  * pass scale = shift = alpha = NULL for f = identity (that is also the backward:
  * dX = pattern(A)^T . dY, called with the transposed CSR).  Neighbours are accumulated in
  * ascending column order per output row.
- * Row tiles: the kernel stages one tile of rows (<= 512) in shared memory per CTA.  With
- * tile_ptr == NULL tiles are uniform; gcs_spmm_build_tiles derives graph-aligned tiles
- * from graph_ptr (whole graphs packed per tile, larger graphs split), which keeps nearly
- * every neighbour of a tile row inside the tile for disjoint batches.  tile_ptr needs
- * gcs_spmm_tile_capacity(n_rows, n_graphs) + 1 int32 entries; *n_tiles_dev is written on
- * the device.  Any matrix structure is accepted either way.
+ * RB8 (optional): gcs_spmm_build_rb8 derives, once per batch, the row-block-of-8 format from
+ * the CSR: per block of 8 consecutive rows the sorted union of their columns, each entry
+ * (col << 8) | mask-of-rows.  Banded residue graphs share most neighbours between consecutive
+ * rows, so a neighbour row is gathered and transformed once per block instead of once per row.
+ * rb8_blk_ptr needs ceil(n_rows/8)+1 int32, rb8_ent nnz uint32 (upper bound), workspace
+ * gcs_spmm_rb8_workspace_bytes(n_rows); n_rows < 2^24.  With rb8_* == NULL the CSR row kernel
+ * runs; results are bit-identical.  Any matrix structure is accepted either way.
  * --------------------------------------------------------------------------------- */
-int32_t gcs_spmm_tile_capacity(int64_t n_rows, int32_t n_graphs);
-int gcs_spmm_build_tiles(const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t* tile_ptr,
-                         int32_t tile_capacity, int32_t* n_tiles_dev, gcs_stream stream);
-int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* tile_ptr,
-                 const int32_t* n_tiles_dev, int64_t n_rows, const float* X, int64_t ldx,
+int64_t gcs_spmm_rb8_workspace_bytes(int64_t n_rows);
+int gcs_spmm_build_rb8(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
+                       int32_t* rb8_blk_ptr, uint32_t* rb8_ent, void* workspace, int64_t workspace_bytes,
+                       gcs_stream stream);
+int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb8_blk_ptr,
+                 const uint32_t* rb8_ent, int64_t n_rows, const float* X, int64_t ldx,
                  const float* scale, const float* shift, const float* alpha, float* Y, int64_t ldy,
                  int32_t H, gcs_stream stream);
 
@@ -212,8 +214,10 @@ typedef struct gcs_batch {
   const float* x;           /* [N, F] */
   int64_t ldx;
   const float* y;           /* [B, C] one-hot; NULL for inference */
-  const int32_t* tile_ptr;    /* row tiles for the aggregation kernels (gcs_spmm_build_tiles), or NULL */
-  const int32_t* n_tiles_dev; /* device scalar written by gcs_spmm_build_tiles, or NULL */
+  const int32_t* rb8_blk_ptr;   /* RB8 form of pattern(A) (gcs_spmm_build_rb8), or NULL */
+  const uint32_t* rb8_ent;
+  const int32_t* rb8_blk_ptr_t; /* RB8 form of pattern(A)^T; may alias when symmetric; backward only */
+  const uint32_t* rb8_ent_t;
 } gcs_batch;
 
 /* Number of floats in the flat trainable / state buffers (layout: gcn-string_b200/params.py). */
