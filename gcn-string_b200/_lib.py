@@ -29,7 +29,7 @@ class Batch(Structure):
     _fields_ = [("n_nodes", c_int64), ("nnz", c_int64), ("n_graphs", c_int32), ("reserved", c_int32),
                 ("rowptr", c_void_p), ("colidx", c_void_p), ("rowptr_t", c_void_p), ("colidx_t", c_void_p),
                 ("graph_ptr", c_void_p), ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p),
-                ("rb8_blk_ptr", c_void_p), ("rb8_ent", c_void_p), ("rb8_blk_ptr_t", c_void_p), ("rb8_ent_t", c_void_p)]
+                ("seg_ids", c_void_p), ("rb8_blk_ptr", c_void_p), ("rb8_ent", c_void_p), ("rb8_blk_ptr_t", c_void_p), ("rb8_ent_t", c_void_p)]
 
 
 P = c_void_p

@@ -259,8 +259,11 @@ namespace tc {   // linear_tc.cu
 bool shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* C, int64_t ldc, const float* bias);
 int64_t split_workspace_bytes(int K, int N);
 int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
-           int64_t M, int K, int N, int accumulate, cudaStream_t st);
+           int64_t M, int K, int N, int accumulate, cudaStream_t st, const float* rowbias = nullptr, int64_t ld_rowbias = 0,
+           const int64_t* seg = nullptr);
 int split(const float* W, int rows, int cols, bool transpose, float* hi, float* lo, cudaStream_t st);
+int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, float* hi, float* lo,
+                  cudaStream_t st);
 bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* dH, int64_t ldh);
 void wgrad_split(int64_t M, int K, int N, int* splits, int* kb_per_split);
 int64_t wgrad_workspace_bytes(int64_t M, int K, int N);
@@ -308,6 +311,48 @@ static int launch_sgemm(const float* P, int64_t ldp, const float* Q, int64_t ldq
   GCS_CHECK_LAUNCH(who);
   return GCS_OK;
 }
+
+namespace gcs {
+
+// Gradient w.r.t. one H-wide block of the concatenated node embedding, all consumers at once:
+//   C[M, Nout] = rowbias[seg[m]] + sum_b  DH_b[M, Hred] . W_b[row_off_b : row_off_b + Nout, 0 : Hred]^T
+// where the DH_b are adjacent column blocks of one buffer (dh, leading dimension ld).  One long-K
+// tensor-core GEMM (no read-modify-write of C) when the shape allows; otherwise the segment
+// broadcast is materialised and the blocks are accumulated one by one on the CUDA cores.
+int dense_dx_concat(const float* dh, int64_t ld, const float* const* W, const int* row_off, int n_blocks, int Hred,
+                    int Nout, const float* rowbias, int64_t ld_rowbias, const int64_t* seg, const int32_t* graph_ptr,
+                    int n_graphs, float* C, int64_t ldc, int64_t M, int accumulate, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t st) {
+  const int Kred = n_blocks * Hred;
+  const bool tc_ok = g_gemm_mode != 1 && n_blocks > 0 && tc::shape_ok(M, Kred, Nout, dh, ld, C, ldc, nullptr) && workspace &&
+                     aligned16(workspace) && workspace_bytes >= tc::split_workspace_bytes(Kred, Nout) &&
+                     (!rowbias || (ld_rowbias % 4 == 0 && aligned16(rowbias)));
+  if (tc_ok) {
+    float* hi = static_cast<float*>(workspace);
+    float* lo = hi + static_cast<int64_t>(Kred) * Nout;
+    for (int b = 0; b < n_blocks; ++b)   // Bt[c][b*Hred + n] = W_b[row_off_b + c][n]
+      GCS_TRY(tc::split_strided(W[b] + static_cast<int64_t>(row_off[b]) * Hred, Nout, Hred, Hred, false, Kred,
+                                hi + static_cast<int64_t>(b) * Hred, lo + static_cast<int64_t>(b) * Hred, st));
+    return tc::launch(dh, ld, hi, lo, nullptr, C, ldc, M, Kred, Nout, accumulate, st, rowbias, ld_rowbias, seg);
+  }
+  // CUDA-core path
+  if (rowbias) {
+    if (accumulate) return fail(GCS_ERR_INVALID_ARGUMENT, "dense_dx_concat: rowbias and accumulate are exclusive");
+    GCS_TRY(gcs_segment_sum_bwd(rowbias, ld_rowbias, graph_ptr, n_graphs, Nout, C, ldc, st));
+  } else if (n_blocks == 0) {
+    return fail(GCS_ERR_INVALID_ARGUMENT, "dense_dx_concat: nothing to compute");
+  }
+  for (int b = 0; b < n_blocks; ++b) {
+    const float* P = dh + static_cast<int64_t>(b) * Hred;
+    const float* Q = W[b] + static_cast<int64_t>(row_off[b]) * Hred;       // [Nout rows][Hred], reduction contiguous
+    const bool vec = Hred % 4 == 0 && Nout % 4 == 0 && ld % 4 == 0 && ldc % 4 == 0 && aligned16(P) && aligned16(Q) && aligned16(C);
+    GCS_TRY((launch_sgemm<true, false>(P, ld, Q, Hred, C, ldc, nullptr, M, Nout, Hred, 1, Hred, (rowbias || accumulate || b > 0) ? 1 : 0, 0,
+                                       vec, st, "dense_dx_concat")));
+  }
+  return GCS_OK;
+}
+
+}  // namespace gcs
 
 extern "C" int64_t gcs_linear_workspace_bytes(int64_t M, int32_t K, int32_t N) {
   (void)M;

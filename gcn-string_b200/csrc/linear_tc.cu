@@ -127,7 +127,8 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cas
 __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
     const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C, int64_t ldc,
-    const float* __restrict__ bias, int64_t M, int K, int accumulate) {
+    const float* __restrict__ bias, int64_t M, int K, int accumulate, const float* __restrict__ rowbias,
+    int64_t ld_rowbias, const int64_t* __restrict__ seg) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t bars = base + kStages * STAGE_BYTES;
@@ -246,6 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int64_t row = static_cast<int64_t>(m0) + r;
+    // optional per-row bias gathered through a segment index: C[row] += rowbias[seg[row]] (the
+    // gradient of the global sum pool, broadcast to the nodes of each graph, fused here)
+    const float* rb = (rowbias && row < M) ? rowbias + __ldg(seg + row) * ld_rowbias + n0 : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32], w[32];
@@ -262,6 +266,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
                                  __uint_as_float(v[4 * q + 3]) + __uint_as_float(w[4 * q + 3]));
           if (bias) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (rb) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + q);
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
           if (accumulate) {
@@ -283,16 +291,19 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
 
 // hi = rna_tf32(w), lo = rna_tf32(w - hi); optionally transposed so that the reduction index
 // is contiguous (the K-major layout the B operand wants).
-__global__ void __launch_bounds__(256) split_weights_kernel(const float* __restrict__ W, int rows, int cols,
-                                                            int transpose, float* __restrict__ hi, float* __restrict__ lo) {
+// W is a [rows, cols] block with row pitch ldw; element (r, c) goes to out[r*ldo + c] or, transposed,
+// to out[c*ldo + r].
+__global__ void __launch_bounds__(256) split_weights_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
+                                                            int transpose, int64_t ldo, float* __restrict__ hi,
+                                                            float* __restrict__ lo) {
   const int64_t n = static_cast<int64_t>(rows) * cols;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<int64_t>(r) * cols);
-    const float w = __ldg(W + i);
+    const float w = __ldg(W + r * ldw + c);
     const float h = __uint_as_float(rna_tf32(w));
     const float l = __uint_as_float(rna_tf32(w - h));
-    const int64_t o = transpose ? static_cast<int64_t>(c) * rows + r : i;
+    const int64_t o = transpose ? c * ldo + r : r * ldo + c;
     hi[o] = h;
     lo[o] = l;
   }
@@ -555,11 +566,15 @@ bool shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float*
          (!bias || aligned16(bias)) && ceil_div(M, BM) <= 65535;
 }
 
+int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, float* hi, float* lo,
+                  cudaStream_t st);
+
 int64_t split_workspace_bytes(int K, int N) { return round_up(2LL * K * N * sizeof(float), 256); }
 
 // Bt: weights already split, laid out [N][K] (reduction contiguous): hi at Bt, lo at Bt + N*K.
 int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
-           int64_t M, int K, int N, int accumulate, cudaStream_t st) {
+           int64_t M, int K, int N, int accumulate, cudaStream_t st, const float* rowbias, int64_t ld_rowbias,
+           const int64_t* seg) {
   alignas(64) CUtensorMap ma, mh, ml;
   GCS_TRY(make_map(&ma, A, M, K, lda, BM));
   GCS_TRY(make_map(&mh, Bt_hi, N, K, K, BN));
@@ -570,7 +585,7 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
     attr = true;
   }
   dim3 grid(N / BN, static_cast<unsigned>(ceil_div(M, BM)));
-  linear_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ma, mh, ml, C, ldc, bias, M, K, accumulate);
+  linear_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ma, mh, ml, C, ldc, bias, M, K, accumulate, rowbias, ld_rowbias, seg);
   GCS_CHECK_LAUNCH("linear_tc_kernel");
   return GCS_OK;
 }
@@ -620,10 +635,15 @@ int wgrad_launch(const float* A, int64_t lda, const float* dH, int64_t ldh, floa
 }
 
 int split(const float* W, int rows, int cols, bool transpose, float* hi, float* lo, cudaStream_t st) {
+  return split_strided(W, rows, cols, cols, transpose, transpose ? rows : cols, hi, lo, st);
+}
+
+int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, float* hi, float* lo,
+                  cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(rows) * cols;
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
-  split_weights_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(W, rows, cols, transpose ? 1 : 0, hi, lo);
+  split_weights_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(W, rows, cols, ldw, transpose ? 1 : 0, ldo, hi, lo);
   GCS_CHECK_LAUNCH("split_weights_kernel");
   return GCS_OK;
 }

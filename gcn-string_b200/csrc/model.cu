@@ -11,14 +11,23 @@
 // and layer k writes the H columns just before the current prefix — layer k's GEMM input
 // is the trailing k*H columns as a strided view (ld = H*(L+1)).  No ConcatV2 copies.  Per
 // dense block only the pre-BatchNorm output h is saved for the backward; BN+PReLU are
-// recomputed (fused into the aggregation's load in the conv blocks).  The backward keeps
-// one gradient buffer gcat of the same shape that the skip connections accumulate into.
+// recomputed (fused into the aggregation's load in the conv blocks).  In the backward the
+// pre-BatchNorm gradients dh_k of the L conv blocks are kept side by side in dhcat[N, H*L]:
+// the gradient of one H-wide block of `cat` is then ONE long-K GEMM over all its consumers
+// (trailing columns of dhcat x the matching row blocks of their kernels) with the pooled
+// gradient broadcast fused into the epilogue - no read-modify-write of a concat-wide buffer.
 // The caller owns the workspace; nothing is allocated here.
 #include <vector>
 
 #include "common.cuh"
 
 namespace gcs {
+
+// linear.cu
+int dense_dx_concat(const float* dh, int64_t ld, const float* const* W, const int* row_off, int n_blocks, int Hred,
+                    int Nout, const float* rowbias, int64_t ld_rowbias, const int64_t* seg, const int32_t* graph_ptr,
+                    int n_graphs, float* C, int64_t ldc, int64_t M, int accumulate, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t st);
 
 struct BlockDesc {
   int k_in, m_out;
@@ -108,9 +117,11 @@ struct Plan {
   void* lin_ws = nullptr;       // split weights of the tensor-core GEMM in flight
   int64_t lin_ws_bytes = 0;
   // backward
-  float* gcat = nullptr;        // [N, Wc]
+  float* gcat = nullptr;        // [N, Wc]  only without pooling (node-level output)
+  float* dhcat = nullptr;       // [N, H*L] dh of the conv blocks, block k at columns [kH, (k+1)H)
   float* tmp_a = nullptr;       // [N, H]
   float* tmp_b = nullptr;       // [N, H]
+  float* tmp_c = nullptr;       // [N, H]   gradient of one block of cat
   float* dlogits = nullptr;     // [rows_post, C]
   float* dpost = nullptr;       // [rows_post, max(H, C)]  dh of a post block
   float* dpost_in = nullptr;    // [rows_post, H]          gradient w.r.t. a post activation
@@ -159,7 +170,7 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
   }
   p.bn_ws_bytes = bn_bytes;
   p.bn_ws = a.take<char>(bn_bytes);
-  int64_t lin_bytes = 0;
+  int64_t lin_bytes = gcs_linear_workspace_bytes(N, p.L * p.H, p.H);     // concatenated input-gradient GEMM
   for (const auto& b : p.blocks) {
     const int64_t v = gcs_linear_workspace_bytes(N, b.k_in, b.m_out);
     if (v > lin_bytes) lin_bytes = v;
@@ -167,9 +178,11 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
   p.lin_ws_bytes = lin_bytes;
   p.lin_ws = a.take<char>(lin_bytes);
   if (training) {
-    p.gcat = a.take<float>(N * p.Wc);
+    if (!c.pool) p.gcat = a.take<float>(N * p.Wc);
+    p.dhcat = a.take<float>(NH * p.L);
     p.tmp_a = a.take<float>(NH);
     p.tmp_b = a.take<float>(NH);
+    p.tmp_c = a.take<float>(NH);
     p.dlogits = a.take<float>(p.rows_post * p.C);
     p.dpost = a.take<float>(p.rows_post * (p.H > p.C ? p.H : p.C));
     p.dpost_in = a.take<float>(p.rows_post * p.H);
@@ -196,6 +209,8 @@ static int check_batch(const gcs_model_config& c, const gcs_batch* b, bool need_
   if (c.pool && (b->n_graphs <= 0 || !b->graph_ptr))
     return fail(GCS_ERR_INVALID_ARGUMENT, "batch: pooling needs n_graphs > 0 and graph_ptr (the batch index i)");
   if (need_labels && !b->y) return fail(GCS_ERR_INVALID_ARGUMENT, "batch: training needs labels y");
+  if (need_transpose && c.pool && !b->seg_ids)
+    return fail(GCS_ERR_INVALID_ARGUMENT, "batch: the backward of the pool needs seg_ids (the batch index i)");
   if (need_transpose && (!b->rowptr_t || (b->nnz > 0 && !b->colidx_t)))
     return fail(GCS_ERR_INVALID_ARGUMENT, "batch: the backward needs the transposed CSR (alias it if symmetric)");
   return GCS_OK;
@@ -326,21 +341,70 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
     da = din;
     ldda = lddin;
   }
-  // ---- pool: dX[n] = dOut[i[n]]
-  if (c.pool) GCS_TIMED("pool_bwd", gcs_segment_sum_bwd(p.dpooled, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.gcat, Wc, st));
-  // ---- message passing, last layer first; skip gradients accumulate into gcat in place
+  // ---- message passing, last layer first.  Block z_k of cat (columns [(L-1-k)H, (L-k)H)) is read by
+  // the pool and by every later conv layer k' > k (rows [(k'-1-k)H, (k'-k)H) of its kernel).
+  const int64_t ldd = static_cast<int64_t>(L) * H;
+  std::vector<const float*> Wp(L);
+  std::vector<int> roff(L);
+  cudaStream_t cst = as_stream(st);
   for (int k = L - 1; k >= 0; --k) {
     const int bi = P + k;
-    const float* dz = p.gcat + static_cast<int64_t>(L - k - 1) * H;
-    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb8_blk_ptr_t, bt.rb8_ent_t, N, dz,
-                                       Wc, nullptr, nullptr, nullptr, p.tmp_a, H, H, st));
-    GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N,
-                           p.cat + static_cast<int64_t>(L - k) * H, Wc, p.tmp_b, H,
-                           p.gcat + static_cast<int64_t>(L - k) * H, Wc, 1, st));
+    const int nb = L - 1 - k;
+    for (int q = 0; q < nb; ++q) {
+      const int kp = k + 1 + q;
+      Wp[q] = params + p.blocks[P + kp].kernel();
+      roff[q] = (kp - 1 - k) * H;
+    }
+    const float* dz;
+    int64_t lddz;
+    if (c.pool) {
+      const float* rb = p.dpooled + static_cast<int64_t>(L - 1 - k) * H;
+      if (nb == 0) {
+        GCS_TIMED("pool_bwd", gcs_segment_sum_bwd(rb, Wc, bt.graph_ptr, bt.n_graphs, H, p.tmp_c, H, st));
+      } else {
+        GCS_TIMED("linear_bwd_input", dense_dx_concat(p.dhcat + static_cast<int64_t>(k + 1) * H, ldd, Wp.data(), roff.data(), nb, H, H,
+                                                      rb, Wc, bt.seg_ids, bt.graph_ptr, bt.n_graphs, p.tmp_c, H, N, 0,
+                                                      p.lin_ws, p.lin_ws_bytes, cst));
+      }
+      dz = p.tmp_c;
+      lddz = H;
+    } else {
+      float* blk = p.gcat + static_cast<int64_t>(L - 1 - k) * H;
+      if (nb > 0)
+        GCS_TIMED("linear_bwd_input", dense_dx_concat(p.dhcat + static_cast<int64_t>(k + 1) * H, ldd, Wp.data(), roff.data(), nb, H, H,
+                                                      nullptr, 0, nullptr, nullptr, 0, blk, Wc, N, 1, p.lin_ws,
+                                                      p.lin_ws_bytes, cst));
+      dz = blk;
+      lddz = Wc;
+    }
+    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb8_blk_ptr_t, bt.rb8_ent_t, N, dz, lddz, nullptr, nullptr,
+                                       nullptr, p.tmp_a, H, H, st));
+    GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N, p.cat + static_cast<int64_t>(L - k) * H, Wc,
+                           p.dhcat + static_cast<int64_t>(k) * H, ldd, nullptr, 0, 0, st));
   }
-  // ---- pre-processing MLP
-  da = p.gcat + static_cast<int64_t>(L) * H;
-  ldda = Wc;
+  // ---- pre-processing MLP: its output block (last H columns of cat) is read by the pool and by
+  // every conv layer k' (rows [k'H, (k'+1)H) of its kernel)
+  for (int kp = 0; kp < L; ++kp) {
+    Wp[kp] = params + p.blocks[P + kp].kernel();
+    roff[kp] = kp * H;
+  }
+  const float* da_pre;
+  int64_t ldda_pre;
+  if (c.pool) {
+    GCS_TIMED("linear_bwd_input", dense_dx_concat(p.dhcat, ldd, Wp.data(), roff.data(), L, H, H, p.dpooled + static_cast<int64_t>(L) * H, Wc,
+                                                  bt.seg_ids, bt.graph_ptr, bt.n_graphs, p.tmp_c, H, N, 0, p.lin_ws,
+                                                  p.lin_ws_bytes, cst));
+    da_pre = p.tmp_c;
+    ldda_pre = H;
+  } else {
+    float* blk = p.gcat + static_cast<int64_t>(L) * H;
+    GCS_TIMED("linear_bwd_input", dense_dx_concat(p.dhcat, ldd, Wp.data(), roff.data(), L, H, H, nullptr, 0, nullptr, nullptr, 0, blk,
+                                                  Wc, N, 1, p.lin_ws, p.lin_ws_bytes, cst));
+    da_pre = blk;
+    ldda_pre = Wc;
+  }
+  da = da_pre;
+  ldda = ldda_pre;
   for (int j = P - 1; j >= 0; --j) {
     const float* in = j == 0 ? bt.x : p.act[j - 1];
     const int64_t ld_in = j == 0 ? bt.ldx : H;

@@ -194,21 +194,25 @@ class GeneralGNN:
             a = SparseAdjacency.from_indices(a.indices, a.dense_shape)
         if a.n_rows != x.shape[0]:
             raise ValueError(f"a is {a.dense_shape} but x has {x.shape[0]} rows")
-        graph_ptr, n_graphs = None, 0
+        graph_ptr, n_graphs, seg = None, 0, None
         if self.cfg.pool is not None:
             if i is None:
                 # upstream: no batch index -> single-graph mode, pool over all nodes
                 graph_ptr = torch.tensor([0, x.shape[0]], dtype=torch.int32, device="cuda")
                 n_graphs = 1
-            elif a.graph_ptr is not None:
-                graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
+                seg = torch.zeros(x.shape[0], dtype=torch.int64, device="cuda")
             else:
                 i = _lib.as_tensor(i)
                 if i.dim() == 2:
                     i = i[:, 0]
-                i = i.to(device="cuda", dtype=torch.int64).contiguous()
-                n_graphs = int(i[-1].item()) + 1 if i.numel() else 0
-                graph_ptr = ops.segment_ptr(i, n_graphs)
+                seg = i.to(device="cuda", dtype=torch.int64).contiguous()
+                if a.graph_ptr is not None:
+                    graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
+                else:
+                    n_graphs = int(seg[-1].item()) + 1 if seg.numel() else 0
+                    graph_ptr = ops.segment_ptr(seg, n_graphs)
+            if seg.shape[0] != x.shape[0]:
+                raise ValueError(f"i has {seg.shape[0]} entries but x has {x.shape[0]} rows")
         elif a.graph_ptr is not None:
             graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
         rp_t, ci_t = a.transposed() if need_transpose else (None, None)
@@ -217,8 +221,8 @@ class GeneralGNN:
         rb8_t = (None, None)     # the prologue-free backward gather is faster on the plain CSR kernel
         batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, 0, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
                            ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None,
-                           ptr(rb8[0]), ptr(rb8[1]), ptr(rb8_t[0]), ptr(rb8_t[1]))
-        keep = (x, a, graph_ptr, rp_t, ci_t, rb8, rb8_t)   # keep device buffers alive
+                           ptr(seg), ptr(rb8[0]), ptr(rb8[1]), ptr(rb8_t[0]), ptr(rb8_t[1]))
+        keep = (x, a, graph_ptr, rp_t, ci_t, rb8, rb8_t, seg)   # keep device buffers alive
         return batch, keep
 
     def _workspace(self, batch, training):

@@ -214,6 +214,7 @@ typedef struct gcs_batch {
   const float* x;           /* [N, F] */
   int64_t ldx;
   const float* y;           /* [B, C] one-hot; NULL for inference */
+  const int64_t* seg_ids;       /* [N] graph id of every node (Spektral's i); needed by the pooled backward */
   const int32_t* rb8_blk_ptr;   /* RB8 form of pattern(A) (gcs_spmm_build_rb8), or NULL */
   const uint32_t* rb8_ent;
   const int32_t* rb8_blk_ptr_t; /* RB8 form of pattern(A)^T; may alias when symmetric; backward only */
