@@ -149,6 +149,7 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
 

@@ -358,7 +358,7 @@ class DisjointLoader:
     """
 
     def __init__(self, dataset, node_level=False, batch_size=1, epochs=None, shuffle=True, rank=0, world_size=1,
-                 want_coo=False, symmetric=None, device_resident=True):
+                 want_coo=False, symmetric=None, device_resident=True, prefetch=None):
         if node_level:
             raise NotImplementedError("node_level=True labels are not built (reference uses graph labels)")
         packed = dataset if isinstance(dataset, PackedGraphs) else pack_graphs(list(dataset))
@@ -373,6 +373,9 @@ class DisjointLoader:
         self.shuffle = shuffle
         self.rank, self.world_size = int(rank), int(world_size)
         self.want_coo = want_coo
+        # one batch ahead on a side stream: the H2D upload (host-resident store) and the batching
+        # kernels of step t+1 overlap the training step t
+        self.prefetch = (not device_resident) if prefetch is None else bool(prefetch)
         self._n = packed.n_graphs
         self._order = np.arange(self._n, dtype=np.int64)
         self._order_dev = None
@@ -400,7 +403,7 @@ class DisjointLoader:
         return ((_Spec((None, f), "float32"), _Spec((None, None), "int64", sparse=True), _Spec((None,), "int64")),
                 _Spec((None, c), "float32"))
 
-    def _slices(self, start, stop):
+    def _slices_of_rank(self, start, stop):
         """This rank's contiguous part of the global slice [start, stop)."""
         if self.world_size == 1:
             return start, stop
@@ -409,7 +412,8 @@ class DisjointLoader:
         lo = start + self.rank * base + min(self.rank, rem)
         return lo, lo + base + (1 if self.rank < rem else 0)
 
-    def _generate(self):
+    def _slices(self):
+        """(device ids, host ids, global batch size) of every step, epoch after epoch."""
         torch = _lib.require_cuda()
         epochs = np.inf if self.epochs is None or self.epochs == -1 else self.epochs
         epoch = 0
@@ -418,13 +422,45 @@ class DisjointLoader:
             if self.shuffle:
                 np.random.shuffle(self._order)
             if self.shuffle or self._order_dev is None:
-                self._order_dev = torch.from_numpy(self._order).cuda()
+                self._order_dev = torch.from_numpy(self._order.copy()).cuda()
+            order_host = self._order.copy()
             for b in range(self.steps_per_epoch):
                 start = b * self.batch_size
                 stop = min(start + self.batch_size, self._n)
-                lo, hi = self._slices(start, stop)
+                lo, hi = self._slices_of_rank(start, stop)
                 if hi <= lo:
                     raise RuntimeError("a data-parallel rank received an empty shard; use batch_size >= world_size")
-                x, a, i, y = self.store.batch(self._order_dev[lo:hi], self._order[lo:hi], want_coo=self.want_coo)
-                a.global_batch_graphs = stop - start
+                yield self._order_dev[lo:hi], order_host[lo:hi], stop - start
+
+    def _launch(self, item, stream):
+        """Enqueue upload + batching kernels for one step on `stream`."""
+        torch = _lib.require_cuda()
+        ids_dev, ids_host, global_count = item
+        with torch.cuda.stream(stream):
+            x, a, i, y = self.store.batch(ids_dev, ids_host, want_coo=self.want_coo)
+            a.global_batch_graphs = global_count
+            event = torch.cuda.Event()
+            event.record(stream)
+        return (x, a, i, y), event
+
+    def _generate(self):
+        torch = _lib.require_cuda()
+        it = self._slices()
+        if not self.prefetch:
+            for item in it:
+                (x, a, i, y), _ = self._launch(item, torch.cuda.current_stream())
                 yield (x, a, i), y
+            return
+        side = torch.cuda.Stream()
+        first = next(it, None)
+        pending = self._launch(first, side) if first is not None else None
+        while pending is not None:
+            (x, a, i, y), event = pending
+            nxt = next(it, None)
+            pending = self._launch(nxt, side) if nxt is not None else None      # step t+1 in flight
+            main = torch.cuda.current_stream()
+            main.wait_event(event)
+            for t in (x, i, y, a.rowptr, a.colidx, a.graph_ptr, a.edge_ptr, a.status, a._indices):
+                if t is not None:
+                    t.record_stream(main)       # allocated on the side stream, consumed on the main one
+            yield (x, a, i), y
