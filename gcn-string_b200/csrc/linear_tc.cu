@@ -18,13 +18,14 @@
 //               [128 x 32] (K-major, 128 B rows, SWIZZLE_128B) per stage, 4 stages
 //   warp 1      MMA issuer (one elected thread): per stage 4 K-steps x 3 tcgen05.mma with the
 //               A operand in TENSOR MEMORY and B from shared memory; owns TMEM alloc/free
-//   warps 2-5   converters: each thread owns one row of the A tile, reads its 128 B from the
+//   warps 2-9   converters: each thread owns half a row of the A tile, reads its 64 B from the
 //               swizzled shared tile (conflict-free), splits hi/lo in registers and writes
 //               both halves into TMEM (tcgen05.st) - the split never touches shared memory,
 //               which the B operand already keeps busy; afterwards the same warps run the
 //               epilogue (tcgen05.ld -> + bias / + C -> 128 B-per-thread row stores)
-// TMEM: columns [0, 128) main accumulator, [128, 256) correction accumulator, [256, 384) two A
-// stages of (32 hi + 32 lo) columns.  The two CTAs that share a row block (N = 256) are adjacent
+// TMEM: columns [0, 128) main accumulator, [128, 256) correction accumulator, [256, 512) four A
+// stages of (32 hi + 32 lo) columns (ncu: with 4 converter warps and 2 stages the tensor pipe was
+// only 58% busy, waiting for the split operand).  The two CTAs that share a row block (N = 256) are adjacent
 // in launch order, so the second read of the A tile is an L2 hit.
 #include <cuda.h>
 
@@ -35,8 +36,10 @@ namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int kStages = 4;    // shared-memory stages (TMA)
-constexpr int kAStages = 2;   // tensor-memory stages of the split A operand
-constexpr int kThreads = 192;
+constexpr int kAStages = 4;   // tensor-memory stages of the split A operand (forward / dX kernel)
+constexpr int kWgAStages = 2; // ... of the weight-gradient kernel (it also keeps a running sum in TMEM)
+constexpr int kConvWarps = 8; // converter warps: two per TMEM lane quarter, 16 of the 32 K columns each
+constexpr int kThreads = 64 + 32 * kConvWarps;
 constexpr uint32_t A_RAW_BYTES = BM * BK * 4;          // 16 KB
 constexpr uint32_t B_BYTES = BN * BK * 4;              // 16 KB per half
 constexpr uint32_t STAGE_BYTES = A_RAW_BYTES + 2 * B_BYTES;
@@ -98,6 +101,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -120,9 +129,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = BM.
+// Instruction descriptor: D = F32, A = B = TF32, both K-major, M = BM, N = BN or 2*BN.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                 (static_cast<uint32_t>(BM >> 4) << 24);
+constexpr uint32_t kInstrDesc2N = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>((2 * BN) >> 3) << 17) |
+                                  (static_cast<uint32_t>(BM >> 4) << 24);
 
 __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
@@ -132,17 +143,21 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t bars = base + kStages * STAGE_BYTES;
-  // barriers (8 B each): full[4] | smem_empty[4] | a_ready[2] | a_empty[2] | acc_full | tmem ptr
+  // barriers (8 B each): full[4] | smem_empty[4] | a_ready[4] | a_empty[4] | acc_full | tmem ptr
   auto full = [&](int s) { return bars + 8u * s; };
   auto smem_empty = [&](int s) { return bars + 32u + 8u * s; };
   auto a_ready = [&](int t) { return bars + 64u + 8u * t; };
-  auto a_empty = [&](int t) { return bars + 80u + 8u * t; };
-  const uint32_t acc_full = bars + 96u;
-  const uint32_t tmem_slot = bars + 104u;
+  auto a_empty = [&](int t) { return bars + 96u + 8u * t; };
+  const uint32_t acc_full = bars + 128u;
+  const uint32_t tmem_slot = bars + 136u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;     // the N tiles of one row block are adjacent in launch order
   const int m0 = blockIdx.y * BM;
+  // Measured on B200 and NOT kept: a 2-CTA cluster with TMA multicast of the weight tiles (same
+  // time: the bound is the ~40 B/clk each SM can ingest, and a multicast byte is still ingested),
+  // 8 vs 4 converter warps, 4 vs 2 tensor-memory stages, 8 vs 12 MMA issues per K block (all within
+  // 2%).  The mainloop runs at ~1220 clk per K block = 48 KB / 39 B/clk; see DESIGN.md 3.2.
   const int num_kb = K / BK;
 
   if (warp == 0 && lane == 0) {
@@ -151,10 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(smem_empty(s), 1 + 4);      // one tcgen05.commit + one arrive per converter warp
+      mbar_init(smem_empty(s), 1 + kConvWarps);   // one tcgen05.commit + one arrive per converter warp
     }
     for (int t = 0; t < kAStages; ++t) {
-      mbar_init(a_ready(t), 128);
+      mbar_init(a_ready(t), 32 * kConvWarps);
       mbar_init(a_empty(t), 1);
     }
     mbar_init(acc_full, 1);
@@ -200,8 +215,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
           // K advance inside the 128 B swizzle atom: +32 B on the start address, +8 TMEM columns
           const uint64_t koff = static_cast<uint64_t>((k * 32) >> 4);
           const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kInstrDesc, acc);        // A_hi . B_hi
-          mma_tf32_ts(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kInstrDesc, acc);        // A_hi . B_lo
+          // One thread issues every MMA and the issue interval (~100 clk) exceeds the 64 clk of an
+          // N = 128 instruction, so A_hi meets BOTH weight halves in one N = 256 instruction: the hi and
+          // lo weight tiles are adjacent in shared memory (one 256-row K-major operand) and the main and
+          // correction accumulators are adjacent in tensor memory.
+          mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kInstrDesc2N, acc);      // A_hi . [B_hi | B_lo]
           mma_tf32_ts(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kInstrDesc, 1u);    // A_lo . B_hi
         }
         tc_commit(smem_empty(s));           // weight tiles of this stage consumed
@@ -212,17 +230,18 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
   } else {
     // ------------------------------------------------------------ converters, then epilogue
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                  // which 16 of the 32 K columns (and, later, output columns)
     const int r = quarter * 32 + lane;                 // row of the tile owned by this thread
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % kStages, t = kb % kAStages;
       mbar_wait(full(s), (kb / kStages) & 1);
       const uint32_t row_addr = base + s * STAGE_BYTES + r * 128;
-      uint32_t hi[32], lo[32];
+      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float4 v;
-        const uint32_t addr = row_addr + ((c ^ (r & 7)) << 4);          // undo the 128 B TMA swizzle
+        const uint32_t addr = row_addr + (((4 * half + c) ^ (r & 7)) << 4);          // undo the 128 B TMA swizzle
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -236,9 +255,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
       if (lane == 0) mbar_arrive(smem_empty(s));       // raw A tile consumed by this warp
       mbar_wait(a_empty(t), ((kb / kAStages) & 1) ^ 1);   // MMAs of the previous use of this TMEM stage are done
       tc_fence_after();
-      const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64;
-      tmem_st32(a_hi, hi);
-      tmem_st32(a_hi + 32, lo);
+      const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64 + 16 * half;
+      tmem_st16(a_hi, hi);
+      tmem_st16(a_hi + 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(a_ready(t));
@@ -251,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
     // gradient of the global sum pool, broadcast to the nodes of each graph, fused here)
     const float* rb = (rowbias && row < M) ? rowbias + __ldg(seg + row) * ld_rowbias + n0 : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
       uint32_t v[32], w[32];
       tmem_ld32(tmem_base + lane_addr + ACC_MAIN + c0, v);
       tmem_ld32(tmem_base + lane_addr + ACC_CORR + c0, w);
@@ -379,7 +398,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
       mbar_init(full(s), 1);
       mbar_init(smem_empty(s), 1);
     }
-    for (int t = 0; t < kAStages; ++t) {
+    for (int t = 0; t < kWgAStages; ++t) {
       mbar_init(a_ready(t), 128);
       mbar_init(a_empty(t), 1);
     }
@@ -413,10 +432,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
   } else if (warp == 1) {
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages, t = kb % kAStages;
+        const int s = kb % kStages, t = kb % kWgAStages;
         const int chain = kb / kWgChain, pos = kb % kWgChain;
         if (pos == 0 && chain > 0) mbar_wait(acc_empty, (chain - 1) & 1);   // accumulators drained
-        mbar_wait(a_ready(t), (kb / kAStages) & 1);     // TMEM A stage and split dH slab are ready
+        mbar_wait(a_ready(t), (kb / kWgAStages) & 1);     // TMEM A stage and split dH slab are ready
         tc_fence_after();
         const uint32_t y_hi = base + s * WG_STAGE_BYTES + WG_X_BYTES;
         const uint64_t d_hi = make_mnmajor_b32_desc(y_hi);
@@ -442,7 +461,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
     const int ct = (warp - 2) * 32 + lane;             // 0..127: share of the dH slab
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % kStages, t = kb % kAStages;
+      const int s = kb % kStages, t = kb % kWgAStages;
       mbar_wait(full(s), (kb / kStages) & 1);
       const uint32_t xs = base + s * WG_STAGE_BYTES;
       uint32_t hi[32], lo[32];
@@ -454,7 +473,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
         hi[m] = h;
         lo[m] = rna_tf32(v - __uint_as_float(h));
       }
-      mbar_wait(a_empty(t), ((kb / kAStages) & 1) ^ 1);
+      mbar_wait(a_empty(t), ((kb / kWgAStages) & 1) ^ 1);
       tc_fence_after();
       const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64;
       tmem_st32(a_hi, hi);
@@ -564,7 +583,7 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t in
 
 bool shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* C, int64_t ldc, const float* bias) {
   return M > 0 && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(C) &&
-         (!bias || aligned16(bias)) && ceil_div(M, BM) <= 65535;
+         (!bias || aligned16(bias)) && ceil_div(M, BM) < 65535;
 }
 
 int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, float* hi, float* lo,
