@@ -83,10 +83,24 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// 1 in exactly one lane of the (converged) warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
+}
+// In-kernel operand split.  ptxas expands cvt.rna.tf32 into ~6 integer/predicate instructions, which made the
+// converter warps' per-K-block chain (~1090 clk) the bound of the mainloop.  Round-to-nearest (ties away, as rna)
+// on the raw bits is two integer instructions; the low part is handed over unrounded - the tensor core ignores the
+// 13 low mantissa bits of a tf32 operand, i.e. truncates it (|lo| <= 2^-11 |x|, so that costs <= 2^-21 |x|).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 #define GCS_R32(v) v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], \
@@ -199,33 +213,36 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    {
+      const uint32_t leader = elect_one();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages, t = kb % kAStages;
         mbar_wait(full(s), (kb / kStages) & 1);        // weight tiles landed
         mbar_wait(a_ready(t), (kb / kAStages) & 1);    // converters filled this TMEM A stage
         tc_fence_after();
-        const uint32_t b_hi = base + s * STAGE_BYTES + A_RAW_BYTES;
-        const uint64_t d_hi = make_kmajor_sw128_desc(b_hi);
-        const uint64_t d_lo = make_kmajor_sw128_desc(b_hi + B_BYTES);
-        const uint32_t a_hi = tmem_base + A_COL + t * 64;
+        if (leader) {
+          const uint32_t b_hi = base + s * STAGE_BYTES + A_RAW_BYTES;
+          const uint64_t d_hi = make_kmajor_sw128_desc(b_hi);
+          const uint32_t a_hi = tmem_base + A_COL + t * 64;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          // K advance inside the 128 B swizzle atom: +32 B on the start address, +8 TMEM columns
-          const uint64_t koff = static_cast<uint64_t>((k * 32) >> 4);
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          // One thread issues every MMA and the issue interval (~100 clk) exceeds the 64 clk of an
-          // N = 128 instruction, so A_hi meets BOTH weight halves in one N = 256 instruction: the hi and
-          // lo weight tiles are adjacent in shared memory (one 256-row K-major operand) and the main and
-          // correction accumulators are adjacent in tensor memory.
-          mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kInstrDesc2N, acc);      // A_hi . [B_hi | B_lo]
-          mma_tf32_ts(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kInstrDesc, 1u);    // A_lo . B_hi
+          for (int k = 0; k < BK / 8; ++k) {
+            // K advance inside the 128 B swizzle atom: +32 B on the start address, +8 TMEM columns
+            const uint64_t koff = static_cast<uint64_t>((k * 32) >> 4);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            // A_hi meets BOTH weight halves in one N = 256 instruction: the hi and lo weight tiles are adjacent in
+            // shared memory (one 256-row K-major operand) and the main and correction accumulators are adjacent in
+            // tensor memory.
+            mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kInstrDesc2N, acc);      // A_hi . [B_hi | B_lo]
+            mma_tf32_ts(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kInstrDesc, 1u);    // A_lo . B_hi
+          }
+          tc_commit(smem_empty(s));           // weight tiles of this stage consumed
+          tc_commit(a_empty(t));              // TMEM A stage consumed
         }
-        tc_commit(smem_empty(s));           // weight tiles of this stage consumed
-        tc_commit(a_empty(t));              // TMEM A stage consumed
+        __syncwarp();
       }
-      tc_commit(acc_full);
+      if (leader) tc_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ converters, then epilogue
@@ -245,11 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t h = rna_tf32(e[i]);
-          hi[4 * c + i] = h;
-          lo[4 * c + i] = rna_tf32(e[i] - __uint_as_float(h));
-        }
+        for (int i = 0; i < 4; ++i) split_tf32(e[i], hi[4 * c + i], lo[4 * c + i]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_empty(s));       // raw A tile consumed by this warp
@@ -305,6 +318,258 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-PAIR variant of the forward / dX kernel (tcgen05 cta_group::2).
+//
+// ncu on the single-CTA kernel above (profiles/r01_gemm_fwd_k1024.md): 12.7 GB of TMA loads per
+// launch at 9.3 TB/s = the ~42 B/clk/SM the L2 -> SM fabric delivers; the tensor pipe waits for
+// the weight tiles, which every CTA streams in full (32 KB of the 48 KB per K block).  A CTA pair
+// computes a 256 x 128 tile with ONE copy of the weight tiles split across the two SMs: each CTA
+// loads its own 128 rows of A (16 KB) and only HALF of the weight rows (64 of B_hi and 64 of B_lo,
+// 16 KB), so the ingest per SM and K block drops from 48 KB to 32 KB for the same tensor work.
+//
+// Per CTA and stage the shared tile is [A raw 128 x 32 | B_hi half 64 x 32 | B_lo half 64 x 32];
+// the two weight halves are adjacent, so the pair-wide B operand of
+//     MMA1:  A_hi . [B_hi(0:64) ; B_lo(0:64) | B_hi(64:128) ; B_lo(64:128)]     N = 256
+// is one 128-row K-major operand per CTA, and
+//     MMA2:  A_lo . [B_hi(0:64) | B_hi(64:128)]                                 N = 128
+// reuses the first 64 rows of it.  Accumulator columns (each CTA, its own 128 rows):
+//     [0,64) main n<64 | [64,128) A_hi.B_lo n<64 | [128,192) main n>=64 | [192,256) A_hi.B_lo n>=64
+//     [256,384) A_lo.B_hi | [384,512) two tensor-memory stages of the split A operand.
+// The leader CTA issues every MMA; the converters of BOTH CTAs arrive on the leader's a_ready
+// barrier (remote mbarrier arrive), tcgen05.commit multicasts the "consumed" signals to both CTAs.
+constexpr int kPStages = 6;
+constexpr int kPAStages = 2;
+constexpr uint32_t P_B_BYTES = 64 * BK * 4;              // 8 KB per weight half
+constexpr uint32_t P_STAGE_BYTES = A_RAW_BYTES + 2 * P_B_BYTES;   // 32 KB
+constexpr uint32_t kPSmemBytes = kPStages * P_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t P_ACC1 = 0, P_ACC2 = 256, P_A_COL = 384;
+// M = 256 across the pair; N = 256 / 128
+constexpr uint32_t kPairDesc256 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
+                                  (static_cast<uint32_t>(256 >> 4) << 24);
+constexpr uint32_t kPairDesc128 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(128 >> 3) << 17) |
+                                  (static_cast<uint32_t>(256 >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {      // arrive on CTA 0's copy of `bar`
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(0));
+  // default semantics (release at CTA scope) as CUTLASS's ClusterBarrier::arrive(cta_id): a .release.cluster arrive compiles to
+  // MEMBAR.ALL.GPU + CCTL.IVALL per arrival (measured: 2100 clk per K block, independent of the tensor work).  What the
+  // leader must observe is ordered without it: the TMEM writes by tcgen05.wait::st + fence::before_thread_sync, the
+  // TMA-written shared tiles never pass through the generic proxy.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_tc_pair_kernel(
+    const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+    const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C, int64_t ldc,
+    const float* __restrict__ bias, int64_t M, int K, int n_tiles, int num_tiles, int accumulate,
+    const float* __restrict__ rowbias, int64_t ld_rowbias, const int64_t* __restrict__ seg) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bars = base + kPStages * P_STAGE_BYTES;
+  // barriers (8 B each): full[6] | smem_empty[6] | a_ready[2] | a_empty[2] | acc_full | tmem ptr
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto smem_empty = [&](int s) { return bars + 48u + 8u * s; };
+  auto a_ready = [&](int t) { return bars + 96u + 8u * t; };
+  auto a_empty = [&](int t) { return bars + 112u + 8u * t; };
+  const uint32_t acc_full = bars + 128u;
+  const uint32_t tmem_slot = bars + 136u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = blockIdx.x;                            // rank in the pair = which 128 rows / which weight half
+  const int num_kb = K / BK;
+  // PERSISTENT: the pair walks tiles pair_id, pair_id + #pairs, ...; tile -> (row pair, N tile) with the N tiles of
+  // one row pair adjacent, so that neighbouring pairs read the same A rows at the same time (L2 hit).  One launch
+  // pays the prologue (barrier init, TMEM allocation, first TMA round trip: ~5k clk) once instead of once per tile
+  // (measured 12k clk of fixed cost per 128 x 128 tile, more than the whole K = 256 mainloop); the TMA producer and
+  // the MMA issuer run ahead into the next tile while the converter warps write the previous tile out.
+  // Every role counts K blocks globally (`it`), which carries the barrier phases across tiles.
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(smem_empty(s), 1 + kConvWarps);    // one multicast tcgen05.commit + one arrive per local converter warp
+    }
+    for (int t = 0; t < kPAStages; ++t) {
+      mbar_init(a_ready(t), 2 * kConvWarps);       // converter warps of both CTAs (only the leader's copy is used)
+      mbar_init(a_empty(t), 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                     // barriers of BOTH CTAs initialised, TMEM allocated
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (each CTA: its rows, its weight halves)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.y; tile < num_tiles; tile += gridDim.y) {
+        const int n0 = (tile % n_tiles) * BN;
+        const int m0 = ((tile / n_tiles) * 2 + rank) * BM;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages;
+          mbar_wait(smem_empty(s), ((it / kPStages) & 1) ^ 1);
+          const uint32_t a_raw = base + s * P_STAGE_BYTES;
+          mbar_arrive_expect_tx(full(s), P_STAGE_BYTES);
+          tma_load_2d(a_raw, &map_a, kb * BK, m0, full(s));
+          tma_load_2d(a_raw + A_RAW_BYTES, &map_b_hi, kb * BK, n0 + 64 * rank, full(s));
+          tma_load_2d(a_raw + A_RAW_BYTES + P_B_BYTES, &map_b_lo, kb * BK, n0 + 64 * rank, full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    // The whole warp walks the loop converged and ONE elected lane issues: under a divergent `if (lane == 0)` ptxas
+    // wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~75 clk per MMA, measured 610 clk per K
+    // block for the eight MMAs - as long as they take to execute).
+    if (rank == 0) {
+      const uint32_t leader = elect_one();
+      uint32_t it = 0;
+      for (int tile = blockIdx.y; tile < num_tiles; tile += gridDim.y) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages, t = it % kPAStages;
+          mbar_wait(full(s), (it / kPStages) & 1);               // this CTA's tiles landed
+          // both CTAs: tiles landed (their converters saw them) and A is in TMEM; for kb == 0 also: the converter
+          // warps have finished reading the previous tile's accumulators (they run its epilogue first)
+          mbar_wait(a_ready(t), (it / kPAStages) & 1);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t d_b = make_kmajor_sw128_desc(base + s * P_STAGE_BYTES + A_RAW_BYTES);
+            const uint32_t a_hi = tmem_base + P_A_COL + t * 64;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * 32) >> 4);
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              mma_tf32_ts_pair(tmem_base + P_ACC1, a_hi + k * 8, d_b + koff, kPairDesc256, acc);        // A_hi . [B_hi ; B_lo]
+              mma_tf32_ts_pair(tmem_base + P_ACC2, a_hi + 32 + k * 8, d_b + koff, kPairDesc128, acc);   // A_lo . B_hi
+            }
+            tc_commit_pair(smem_empty(s));
+            tc_commit_pair(a_empty(t));
+            if (kb == num_kb - 1) tc_commit_pair(acc_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ converters, then epilogue, per tile
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t it = 0, tile_iter = 0;
+    for (int tile = blockIdx.y; tile < num_tiles; tile += gridDim.y, ++tile_iter) {
+      const int n0 = (tile % n_tiles) * BN;
+      const int64_t m0 = (static_cast<int64_t>(tile / n_tiles) * 2 + rank) * BM;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kPStages, t = it % kPAStages;
+        mbar_wait(full(s), (it / kPStages) & 1);
+        const uint32_t row_addr = base + s * P_STAGE_BYTES + r * 128;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 v;
+          const uint32_t addr = row_addr + (((4 * half + c) ^ (r & 7)) << 4);          // undo the 128 B TMA swizzle
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(e[i], hi[4 * c + i], lo[4 * c + i]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_empty(s));
+        mbar_wait(a_empty(t), ((it / kPAStages) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_hi = tmem_base + lane_addr + P_A_COL + t * 64 + 16 * half;
+        tmem_st16(a_hi, hi);
+        tmem_st16(a_hi + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(a_ready(t));
+      }
+      mbar_wait(acc_full, tile_iter & 1);
+      tc_fence_after();
+      const int64_t row = m0 + r;
+      const float* rb = (rowbias && row < M) ? rowbias + __ldg(seg + row) * ld_rowbias + n0 : nullptr;
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        uint32_t v[32], w[32], u[32];
+        const uint32_t mcol = c0 < 64 ? c0 : 64 + c0;        // [0,64) -> [0,64), [64,128) -> [128,192)
+        tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol, v);
+        tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol + 64, w);
+        tmem_ld32(tmem_base + lane_addr + P_ACC2 + c0, u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+          float* cp = C + row * ldc + n0 + c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(__uint_as_float(v[4 * q]) + (__uint_as_float(w[4 * q]) + __uint_as_float(u[4 * q])),
+                                   __uint_as_float(v[4 * q + 1]) + (__uint_as_float(w[4 * q + 1]) + __uint_as_float(u[4 * q + 1])),
+                                   __uint_as_float(v[4 * q + 2]) + (__uint_as_float(w[4 * q + 2]) + __uint_as_float(u[4 * q + 2])),
+                                   __uint_as_float(v[4 * q + 3]) + (__uint_as_float(w[4 * q + 3]) + __uint_as_float(u[4 * q + 3])));
+            if (bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (rb) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + q);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(cp + 4 * q);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(cp + 4 * q) = o;
+          }
+        }
+      }
+      tc_fence_before();          // accumulator reads ordered before this warp's next a_ready arrive
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();              // the peer's tensor core may still read this CTA's shared memory until its commits land
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
 }
 
@@ -430,13 +695,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages, t = kb % kWgAStages;
-        const int chain = kb / kWgChain, pos = kb % kWgChain;
-        if (pos == 0 && chain > 0) mbar_wait(acc_empty, (chain - 1) & 1);   // accumulators drained
-        mbar_wait(a_ready(t), (kb / kWgAStages) & 1);     // TMEM A stage and split dH slab are ready
-        tc_fence_after();
+    const uint32_t leader = elect_one();             // converged warp, one elected lane issues (see linear_tc_kernel)
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages, t = kb % kWgAStages;
+      const int chain = kb / kWgChain, pos = kb % kWgChain;
+      if (pos == 0 && chain > 0) mbar_wait(acc_empty, (chain - 1) & 1);   // accumulators drained
+      mbar_wait(a_ready(t), (kb / kWgAStages) & 1);     // TMEM A stage and split dH slab are ready
+      tc_fence_after();
+      if (leader) {
         const uint32_t y_hi = base + s * WG_STAGE_BYTES + WG_X_BYTES;
         const uint64_t d_hi = make_mnmajor_b32_desc(y_hi);
         const uint64_t d_lo = make_mnmajor_b32_desc(y_hi + WG_Y_BYTES);
@@ -453,6 +719,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
         tc_commit(a_empty(t));
         if (pos == kWgChain - 1 || kb == num_kb - 1) tc_commit(acc_full);
       }
+      __syncwarp();
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------ converters
@@ -469,9 +736,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
       for (int m = 0; m < 32; ++m) {
         float v;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (m * 128 + i) * 4));
-        const uint32_t h = rna_tf32(v);
-        hi[m] = h;
-        lo[m] = rna_tf32(v - __uint_as_float(h));
+        split_tf32(v, hi[m], lo[m]);
       }
       mbar_wait(a_empty(t), ((kb / kWgAStages) & 1) ^ 1);
       tc_fence_after();
@@ -485,10 +750,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
         const uint32_t addr = ys + (ct + 128 * u) * 16;
         float4 v;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-        const float hx = __uint_as_float(rna_tf32(v.x)), hy = __uint_as_float(rna_tf32(v.y));
-        const float hz = __uint_as_float(rna_tf32(v.z)), hw = __uint_as_float(rna_tf32(v.w));
-        const float lx = __uint_as_float(rna_tf32(v.x - hx)), ly = __uint_as_float(rna_tf32(v.y - hy));
-        const float lz = __uint_as_float(rna_tf32(v.z - hz)), lw = __uint_as_float(rna_tf32(v.w - hw));
+        uint32_t h4[4], l4[4];
+        split_tf32(v.x, h4[0], l4[0]); split_tf32(v.y, h4[1], l4[1]);
+        split_tf32(v.z, h4[2], l4[2]); split_tf32(v.w, h4[3], l4[3]);
+        const float hx = __uint_as_float(h4[0]), hy = __uint_as_float(h4[1]), hz = __uint_as_float(h4[2]), hw = __uint_as_float(h4[3]);
+        const float lx = __uint_as_float(l4[0]), ly = __uint_as_float(l4[1]), lz = __uint_as_float(l4[2]), lw = __uint_as_float(l4[3]);
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + WG_Y_BYTES), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
       }
@@ -591,12 +857,32 @@ int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpos
 
 int64_t split_workspace_bytes(int K, int N) { return round_up(2LL * K * N * sizeof(float), 256); }
 
+static int g_pair_mode = 1;                               // 1 = CTA-pair kernel (default), 0 = single-CTA kernel
+void set_pair_mode(int m) { g_pair_mode = m; }
+
 // Bt: weights already split, laid out [N][K] (reduction contiguous): hi at Bt, lo at Bt + N*K.
 int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
            int64_t M, int K, int N, int accumulate, cudaStream_t st, const float* rowbias, int64_t ld_rowbias,
            const int64_t* seg) {
   alignas(64) CUtensorMap ma, mh, ml;
   GCS_TRY(make_map(&ma, A, M, K, lda, BM));
+  if (g_pair_mode && ceil_div(M, 2 * BM) * (N / BN) < (1LL << 30)) {
+    GCS_TRY(make_map(&mh, Bt_hi, N, K, K, 64));
+    GCS_TRY(make_map(&ml, Bt_lo, N, K, K, 64));
+    static bool attr2 = false;
+    if (!attr2) {
+      GCS_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
+      attr2 = true;
+    }
+    const int n_tiles = N / BN;
+    const int num_tiles = static_cast<int>(ceil_div(M, 2 * BM)) * n_tiles;
+    const int pairs = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;      // persistent: one CTA pair per SM pair
+    dim3 grid(2, pairs);                                                           // x = rank in the pair
+    linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, C, ldc, bias, M, K, n_tiles, num_tiles, accumulate,
+                                                               rowbias, ld_rowbias, seg);
+    GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
+    return GCS_OK;
+  }
   GCS_TRY(make_map(&mh, Bt_hi, N, K, K, BN));
   GCS_TRY(make_map(&ml, Bt_lo, N, K, K, BN));
   static bool attr = false;
