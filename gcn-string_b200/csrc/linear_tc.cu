@@ -341,11 +341,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
 //     [256,384) A_lo.B_hi | [384,512) two tensor-memory stages of the split A operand.
 // The leader CTA issues every MMA; the converters of BOTH CTAs arrive on the leader's a_ready
 // barrier (remote mbarrier arrive), tcgen05.commit multicasts the "consumed" signals to both CTAs.
-constexpr int kPStages = 6;
+constexpr int kPStages = 5;
 constexpr int kPAStages = 2;
 constexpr uint32_t P_B_BYTES = 64 * BK * 4;              // 8 KB per weight half
 constexpr uint32_t P_STAGE_BYTES = A_RAW_BYTES + 2 * P_B_BYTES;   // 32 KB
-constexpr uint32_t kPSmemBytes = kPStages * P_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t P_OUT_BYTES = 32 * 32 * 4;            // per converter warp: one 32 x 32 output box staged for the TMA store
+constexpr uint32_t kPSmemBytes = kPStages * P_STAGE_BYTES + kConvWarps * P_OUT_BYTES + 1024 + 256;
 constexpr uint32_t P_ACC1 = 0, P_ACC2 = 256, P_A_COL = 384;
 // M = 256 across the pair; N = 256 / 128
 constexpr uint32_t kPairDesc256 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
@@ -387,14 +388,24 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_tc_pair_kernel(
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
-    const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C, int64_t ldc,
+    const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_c,
     const float* __restrict__ bias, int64_t M, int K, int n_tiles, int num_tiles, int accumulate,
     const float* __restrict__ rowbias, int64_t ld_rowbias, const int64_t* __restrict__ seg) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t bars = base + kPStages * P_STAGE_BYTES;
+  const uint32_t out_stage = base + kPStages * P_STAGE_BYTES;       // 1024 B aligned (stages are 32 KB)
+  const uint32_t bars = out_stage + kConvWarps * P_OUT_BYTES;
   // barriers (8 B each): full[6] | smem_empty[6] | a_ready[2] | a_empty[2] | acc_full | tmem ptr
   auto full = [&](int s) { return bars + 8u * s; };
   auto smem_empty = [&](int s) { return bars + 48u + 8u * s; };
@@ -417,6 +428,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c));
     for (int s = 0; s < kPStages; ++s) {
       mbar_init(full(s), 1);
       mbar_init(smem_empty(s), 1 + kConvWarps);    // one multicast tcgen05.commit + one arrive per local converter warp
@@ -530,6 +542,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
       tc_fence_after();
       const int64_t row = m0 + r;
       const float* rb = (rowbias && row < M) ? rowbias + __ldg(seg + row) * ld_rowbias + n0 : nullptr;
+      // Each warp writes its 32 x 32 boxes through shared memory and a TMA store (a reduce-add store when the
+      // result accumulates into C): row-per-thread global stores touch 32 lines per instruction (4096 LSU wavefronts
+      // per tile; ncu: the tensor pipe idled ~7 k clk per tile behind them), the staged box is eight conflict-free
+      // 128-bit shared stores per thread and one bulk copy that drains while the warp is already converting the
+      // next tile.  Rows past M are clipped by the tensor map.
+      const uint32_t sbuf = out_stage + (warp - 2) * P_OUT_BYTES;
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t v[32], w[32], u[32];
@@ -537,33 +555,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
         tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol, v);
         tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol + 64, w);
         tmem_ld32(tmem_base + lane_addr + P_ACC2 + c0, u);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has left this buffer
+        __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < M) {
-          float* cp = C + row * ldc + n0 + c0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(__uint_as_float(v[4 * q]) + (__uint_as_float(w[4 * q]) + __uint_as_float(u[4 * q])),
-                                   __uint_as_float(v[4 * q + 1]) + (__uint_as_float(w[4 * q + 1]) + __uint_as_float(u[4 * q + 1])),
-                                   __uint_as_float(v[4 * q + 2]) + (__uint_as_float(w[4 * q + 2]) + __uint_as_float(u[4 * q + 2])),
-                                   __uint_as_float(v[4 * q + 3]) + (__uint_as_float(w[4 * q + 3]) + __uint_as_float(u[4 * q + 3])));
-            if (bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (rb) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + q);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(cp + 4 * q);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            *reinterpret_cast<float4*>(cp + 4 * q) = o;
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(__uint_as_float(v[4 * q]) + (__uint_as_float(w[4 * q]) + __uint_as_float(u[4 * q])),
+                                 __uint_as_float(v[4 * q + 1]) + (__uint_as_float(w[4 * q + 1]) + __uint_as_float(u[4 * q + 1])),
+                                 __uint_as_float(v[4 * q + 2]) + (__uint_as_float(w[4 * q + 2]) + __uint_as_float(u[4 * q + 2])),
+                                 __uint_as_float(v[4 * q + 3]) + (__uint_as_float(w[4 * q + 3]) + __uint_as_float(u[4 * q + 3])));
+          if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
+          if (rb) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + q);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          const uint32_t dst = sbuf + lane * 128 + ((q ^ (lane & 7)) << 4);          // SWIZZLE_128B box layout
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          const int crow = static_cast<int>(m0) + quarter * 32;
+          if (crow < M) {
+            if (accumulate) tma_reduce_add_2d(&map_c, sbuf, n0 + c0, crow);
+            else tma_store_2d(&map_c, sbuf, n0 + c0, crow);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();          // accumulator reads ordered before this warp's next a_ready arrive
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");           // every box written before the CTA exits
   }
   tc_fence_before();
   cluster_sync_all();              // the peer's tensor core may still read this CTA's shared memory until its commits land
@@ -864,11 +889,12 @@ void set_pair_mode(int m) { g_pair_mode = m; }
 int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
            int64_t M, int K, int N, int accumulate, cudaStream_t st, const float* rowbias, int64_t ld_rowbias,
            const int64_t* seg) {
-  alignas(64) CUtensorMap ma, mh, ml;
+  alignas(64) CUtensorMap ma, mh, ml, mc;
   GCS_TRY(make_map(&ma, A, M, K, lda, BM));
   if (g_pair_mode && ceil_div(M, 2 * BM) * (N / BN) < (1LL << 30)) {
     GCS_TRY(make_map(&mh, Bt_hi, N, K, K, 64));
     GCS_TRY(make_map(&ml, Bt_lo, N, K, K, 64));
+    GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));        // output boxes of 32 rows x 32 columns (128 B rows, SWIZZLE_128B)
     static bool attr2 = false;
     if (!attr2) {
       GCS_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
@@ -878,7 +904,7 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
     const int num_tiles = static_cast<int>(ceil_div(M, 2 * BM)) * n_tiles;
     const int pairs = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;      // persistent: one CTA pair per SM pair
     dim3 grid(2, pairs);                                                           // x = rank in the pair
-    linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, C, ldc, bias, M, K, n_tiles, num_tiles, accumulate,
+    linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, bias, M, K, n_tiles, num_tiles, accumulate,
                                                                rowbias, ld_rowbias, seg);
     GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
     return GCS_OK;
