@@ -193,7 +193,48 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(
       be[k] = __ldg(beta + c + k);
       al[k] = alpha ? __ldg(alpha + c + k) : 1.f;
     }
-    for (int64_t r = rb + warp; r < re; r += 8) {
+    // Four rows per step: their contributions are formed and pre-summed in fp32 and folded into the fp64 column
+    // accumulators once per step.  One F2F + DADD/DFMA per element made this pass conversion-bound (331 us for
+    // 1.06 GB = 3.2 TB/s; the fp64-accumulating statistics pass with a third of the conversions runs at 7.3 TB/s);
+    // a four-term fp32 partial sum costs ~1e-7 relative, far inside the 1e-5 budget.
+    auto term = [&](float hvk, float gvk, int k, float& t1, float& t2, float& t3) {
+      const float xhat = (hvk - mu[k]) * rs[k];
+      const float z = fmaf(ga[k], xhat, be[k]);
+      float dz = gvk;
+      t3 = 0.f;
+      if (alpha) {
+        dz = z > 0.f ? gvk : (z < 0.f ? gvk * al[k] : 0.f);
+        t3 = gvk * fminf(z, 0.f);
+      }
+      t1 = dz;
+      t2 = dz * xhat;
+    };
+    int64_t r = rb + warp;
+    for (; r + 24 < re; r += 32) {
+      float hv[4][VEC], gv[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (VEC == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(h + (r + 8 * u) * ldh + c));
+          const float4 g = __ldg(reinterpret_cast<const float4*>(da + (r + 8 * u) * ldda + c));
+          hv[u][0] = t.x; hv[u][1] = t.y; hv[u][2] = t.z; hv[u][3] = t.w;
+          gv[u][0] = g.x; gv[u][1] = g.y; gv[u][2] = g.z; gv[u][3] = g.w;
+        } else {
+          hv[u][0] = __ldg(h + (r + 8 * u) * ldh + c);
+          gv[u][0] = __ldg(da + (r + 8 * u) * ldda + c);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        float a1[4], a2[4], a3[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) term(hv[u][k], gv[u][k], k, a1[u], a2[u], a3[u]);
+        acc[3 * k] += static_cast<double>((a1[0] + a1[1]) + (a1[2] + a1[3]));
+        acc[3 * k + 1] += static_cast<double>((a2[0] + a2[1]) + (a2[2] + a2[3]));
+        if (alpha) acc[3 * k + 2] += static_cast<double>((a3[0] + a3[1]) + (a3[2] + a3[3]));
+      }
+    }
+    for (; r < re; r += 8) {
       float hv[VEC], gv[VEC];
       if (VEC == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
@@ -206,15 +247,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(
       }
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const float xhat = (hv[k] - mu[k]) * rs[k];
-        const float z = fmaf(ga[k], xhat, be[k]);
-        float dz = gv[k];
-        if (alpha) {
-          dz = z > 0.f ? gv[k] : (z < 0.f ? gv[k] * al[k] : 0.f);
-          acc[3 * k + 2] += static_cast<double>(gv[k] * fminf(z, 0.f));
-        }
-        acc[3 * k] += static_cast<double>(dz);
-        acc[3 * k + 1] = fma(static_cast<double>(dz), static_cast<double>(xhat), acc[3 * k + 1]);
+        float t1, t2, t3;
+        term(hv[k], gv[k], k, t1, t2, t3);
+        acc[3 * k] += static_cast<double>(t1);
+        acc[3 * k + 1] += static_cast<double>(t2);
+        if (alpha) acc[3 * k + 2] += static_cast<double>(t3);
       }
     }
   }
