@@ -364,6 +364,8 @@ class DisjointLoader:
         packed = dataset if isinstance(dataset, PackedGraphs) else pack_graphs(list(dataset))
         if packed.n_graphs == 0:
             raise ValueError("Datasets cannot be empty")
+        if symmetric is None:
+            symmetric = getattr(packed, "symmetric", None)      # recorded by the shard writer (shards.py)
         self.dataset = dataset
         # device_resident=False keeps the dataset in pinned host memory and uploads per batch
         self.store = (DeviceGraphStore if device_resident else HostGraphStore)(packed, symmetric=symmetric)

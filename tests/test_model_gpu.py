@@ -288,3 +288,59 @@ def test_loader_epochs_shuffle_and_short_last_batch():
         parts.append([host(y) for (_, _, _), y in ld])
     assert np.array_equal(np.concatenate([parts[0][0], parts[1][0]]), ds.y[:5])
     assert parts[0][0].shape[0] == 3 and parts[1][0].shape[0] == 2
+
+
+def test_loader_over_shards_equals_loader_over_graphs(tmp_path):
+    """§8 f1: a dataset converted to packed shards (shards.write_dataset) and memory-mapped back
+    drives the loader to bit-identical batches, from HBM and from pinned host memory."""
+    from gcn_string_b200 import shards
+    ds = synthetic.make_dataset(10, seed=21, n_mean=40, deg=8, n_feat=6)
+    graphs = [g.Graph(*ds.graph(k)[:2], y=ds.graph(k)[2]) for k in range(10)]
+    shards.write_dataset(graphs, str(tmp_path / "s"), graphs_per_shard=4)
+    packed = shards.load_dataset(str(tmp_path / "s"), verify=True)
+    assert packed.symmetric
+    for resident in (True, False):
+        la = g.DisjointLoader(g.Dataset.from_graphs(graphs), batch_size=4, epochs=1, shuffle=False, want_coo=True)
+        lb = g.DisjointLoader(packed, batch_size=4, epochs=1, shuffle=False, want_coo=True, device_resident=resident)
+        n = 0
+        for ((xa, aa, ia), ya), ((xb, ab, ib), yb) in zip(la, lb):
+            assert torch.equal(xa, xb) and torch.equal(ia, ib) and torch.equal(ya, yb)
+            assert torch.equal(aa.rowptr, ab.rowptr) and torch.equal(aa.colidx, ab.colidx)
+            assert torch.equal(aa.indices, ab.indices) and torch.equal(aa.graph_ptr, ab.graph_ptr)
+            assert ab.symmetric                    # taken from the shard header, no device check needed
+            n += 1
+        assert n == 3
+
+
+def test_evaluate_pass_matches_oracle_and_sklearn(small_case):
+    """§8 f2: evaluate(loader) of gcn.py:342-362 - inference forward on moving statistics, loss and
+    accuracy weighted by batch size, per-batch predictions - and the ROC numbers the reference plots."""
+    skm = pytest.importorskip("sklearn.metrics")
+    from gcn_string_b200.evaluate import evaluate, positive_scores, roc_auc, roc_curve
+    c = small_case
+    cfg = c["cfg"]
+    model = make_model(cfg, c["w"], c["s"])
+    ds = c["ds"]
+    loader = g.DisjointLoader(ds, batch_size=3, epochs=None, shuffle=False)
+    (loss, acc), preds = evaluate(model, loader)
+    assert [p.shape[0] for p in preds] == [3, 3, 2]
+    # oracle: per batch, inference mode
+    losses, accs, sizes, probs_ref = [], [], [], []
+    for b0 in range(0, 8, 3):
+        ids = list(range(b0, min(b0 + 3, 8)))
+        (xr, (idx, _, _), seg), yr = batching_ref.collate([ds.graph(k) for k in ids])
+        probs, cache = O1.forward(cfg, c["specs"], c["w"], c["s"], xr, idx[:, 0], idx[:, 1], seg, len(ids), training=False)
+        probs_ref.append(probs)
+        losses.append(O1.xent_from_logits(cache["logits"], yr.astype(np.float64))[0])
+        accs.append(O1.accuracy(probs, yr))
+        sizes.append(len(ids))
+    want = np.average(np.array([losses, accs], dtype=np.float64).T, 0, weights=sizes)
+    assert abs(loss - want[0]) < TOL * abs(want[0]) and abs(acc - want[1]) < 1e-6
+    got = np.concatenate([host(p) for p in preds])
+    assert rel_err(got, np.concatenate(probs_ref)) < TOL
+    scores = positive_scores(preds)
+    labels = ds.y[:, 1]
+    fpr, tpr, _ = roc_curve(labels, scores)
+    f0, t0, _ = skm.roc_curve(labels, host(scores).astype(np.float64))
+    assert np.allclose(fpr, f0) and np.allclose(tpr, t0)
+    assert abs(roc_auc(labels, scores) - skm.roc_auc_score(labels, host(scores).astype(np.float64))) < 1e-9
