@@ -623,23 +623,23 @@ __global__ void __launch_bounds__(256) split_weights_kernel(const float* __restr
 //
 // The reduction runs over the M rows, both operands are activations (split on the fly) and both
 // are stored with the reduction index as the SLOW dimension.  One CTA = one 128 x 128 tile of dW
-// over a range of rows, 320 threads:
+// over a range of rows, 448 threads:
 //   warp 0      TMA: per 32-row step the raw A slab [32 x 128] (no swizzle) and the raw dH slab as
 //               four [32 x 32] boxes (SWIZZLE_128B_ATOM_32B = the canonical MN-major fp32 layout)
 //   warp 1      MMA issuer: A^T from tensor memory (K-major by construction), dH from shared
-//               memory as an MN-major operand; 3 MMAs per K=8 step into main / correction
-//               accumulators; owns TMEM
-//   warps 2-5   converters: thread i gathers column i of the A slab (32 conflict-free scalar
-//               loads: the transpose is free), splits it and writes both halves into TMEM; the dH
-//               slab is split element-wise in place (hi) + a second buffer (lo), then
-//               fence.proxy.async hands it to the tensor core
-//   warps 6-9   accumulators: every 16 steps (512 rows) they fold main + correction into a
+//               memory as an MN-major operand; 2 MMAs per K=8 step (N = 256 into [main | correction],
+//               N = 128 into correction); owns TMEM
+//   warps 2-5   A^T converters: thread i gathers column i of the A slab (32 conflict-free scalar
+//               loads: the transpose is free), splits it and writes both halves into TMEM
+//   warps 6-9   dH splitters: the slab is split element-wise in place (hi) + the buffer right behind
+//               it (lo), then fence.proxy.async hands both to the tensor core
+//   warps 10-13 accumulators: every 16 steps (512 rows) they fold main + correction into a
 //               running fp32 sum kept in TMEM columns [384, 512) with round-to-nearest adds, so
 //               that no truncating tensor-core chain is longer than 128 K-steps; at the end they
 //               write the CTA's partial tile.  Partials are summed in a fixed order afterwards.
 static int g_wg_chain = 16;                              // K blocks (of 32 rows) per tensor-core accumulation chain
 void set_wgrad_chain(int c) { if (c > 0) g_wg_chain = c; }
-constexpr int kWgThreads = 320;
+constexpr int kWgThreads = 448;
 constexpr uint32_t WG_X_BYTES = 32 * 128 * 4;            // 16 KB raw A slab
 constexpr uint32_t WG_Y_BYTES = 32 * 128 * 4;            // 16 KB dH slab (hi in place) ; + 16 KB lo
 constexpr uint32_t WG_STAGE_BYTES = WG_X_BYTES + 2 * WG_Y_BYTES;
@@ -648,6 +648,8 @@ constexpr uint32_t RUN_COL = 384;
 // D = F32, A = B = TF32, A K-major (TMEM), B MN-major, N = 128, M = 128
 constexpr uint32_t kWgInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | (static_cast<uint32_t>(128 >> 3) << 17) |
                                   (static_cast<uint32_t>(128 >> 4) << 24);
+constexpr uint32_t kWgInstrDesc2N = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | (static_cast<uint32_t>(256 >> 3) << 17) |
+                                    (static_cast<uint32_t>(128 >> 4) << 24);
 
 // MN-major fp32 operand, SWIZZLE_128B_BASE32B: 128 B rows (32 elements along N), 4-row swizzle
 // groups 512 B apart along K, 32-column boxes 4096 B apart along N.
@@ -673,6 +675,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
   auto a_ready = [&](int t) { return bars + 64u + 8u * t; };
   auto a_empty = [&](int t) { return bars + 80u + 8u * t; };
   const uint32_t acc_full = bars + 96u, acc_empty = bars + 104u, tmem_slot = bars + 112u;
+  auto y_ready = [&](int s) { return bars + 120u + 8u * s; };      // dH slab of smem stage s is split
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 128, j0 = blockIdx.y * 128;
@@ -687,6 +690,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full(s), 1);
       mbar_init(smem_empty(s), 1);
+      mbar_init(y_ready(s), 128);
     }
     for (int t = 0; t < kWgAStages; ++t) {
       mbar_init(a_ready(t), 128);
@@ -725,19 +729,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
       const int s = kb % kStages, t = kb % kWgAStages;
       const int chain = kb / kWgChain, pos = kb % kWgChain;
       if (pos == 0 && chain > 0) mbar_wait(acc_empty, (chain - 1) & 1);   // accumulators drained
-      mbar_wait(a_ready(t), (kb / kWgAStages) & 1);     // TMEM A stage and split dH slab are ready
+      mbar_wait(a_ready(t), (kb / kWgAStages) & 1);     // A^T of this step is in tensor memory
+      mbar_wait(y_ready(s), (kb / kStages) & 1);        // dH slab of this step is split (hi in place, lo right behind it)
       tc_fence_after();
       if (leader) {
         const uint32_t y_hi = base + s * WG_STAGE_BYTES + WG_X_BYTES;
         const uint64_t d_hi = make_mnmajor_b32_desc(y_hi);
-        const uint64_t d_lo = make_mnmajor_b32_desc(y_hi + WG_Y_BYTES);
         const uint32_t a_hi = tmem_base + A_COL + t * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t koff = static_cast<uint64_t>((k * 8 * 128) >> 4);       // 8 rows of 128 B per K step
           const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
-          mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kWgInstrDesc, acc);
-          mma_tf32_ts(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kWgInstrDesc, acc);
+          // The lo slab lies right behind the hi slab, i.e. [dH_hi | dH_lo] is ONE MN-major operand of eight 32-column
+          // boxes: A_hi meets both in a single N = 256 instruction whose accumulator is [main | correction]; A_lo . dH_hi
+          // then adds into the correction half (in-order execution).  Eight instead of twelve issues per K block.
+          mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kWgInstrDesc2N, acc);
           mma_tf32_ts(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kWgInstrDesc, 1u);
         }
         tc_commit(smem_empty(s));
@@ -747,10 +753,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
       __syncwarp();
     }
   } else if (warp < 6) {
-    // ------------------------------------------------------------ converters
+    // ------------------------------------------------------------ A^T converters: column i of the A slab -> TMEM
     const int quarter = warp & 3;
     const int i = quarter * 32 + lane;                 // output row (column of the A slab) owned by this thread
-    const int ct = (warp - 2) * 32 + lane;             // 0..127: share of the dH slab
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % kStages, t = kb % kWgAStages;
@@ -768,8 +773,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
       const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64;
       tmem_st32(a_hi, hi);
       tmem_st32(a_hi + 32, lo);
-      // dH slab: hi in place, lo into the second buffer (element-wise, layout-agnostic)
-      const uint32_t ys = xs + WG_X_BYTES;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(a_ready(t));
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ dH splitters: hi in place, lo into the buffer
+    // right behind it (element-wise, layout-agnostic).  Their own warps and their own barrier per shared-memory
+    // stage: a clock64 trace of the one-role version showed the converter chain (gather 200 + TMEM store 160 + dH
+    // split 500 + fences, ~1150 clk per K block) AND the issuing thread (twelve MMAs, three commits) both longer than
+    // the 768 clk of tensor work.  (Also measured, not kept: a separate ring for the split operand so that landing
+    // stages recycle without waiting for the tensor core - 4% slower.)
+    const int ct = (warp - 6) * 32 + lane;             // 0..127: share of the dH slab
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(full(s), (kb / kStages) & 1);
+      const uint32_t ys = base + s * WG_STAGE_BYTES + WG_X_BYTES;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const uint32_t addr = ys + (ct + 128 * u) * 16;
@@ -778,15 +797,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
         uint32_t h4[4], l4[4];
         split_tf32(v.x, h4[0], l4[0]); split_tf32(v.y, h4[1], l4[1]);
         split_tf32(v.z, h4[2], l4[2]); split_tf32(v.w, h4[3], l4[3]);
-        const float hx = __uint_as_float(h4[0]), hy = __uint_as_float(h4[1]), hz = __uint_as_float(h4[2]), hw = __uint_as_float(h4[3]);
-        const float lx = __uint_as_float(l4[0]), ly = __uint_as_float(l4[1]), lz = __uint_as_float(l4[2]), lw = __uint_as_float(l4[3]);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + WG_Y_BYTES), "f"(lx), "f"(ly), "f"(lz), "f"(lw) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h4[0]), "r"(h4[1]), "r"(h4[2]), "r"(h4[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + WG_Y_BYTES), "r"(l4[0]), "r"(l4[1]), "r"(l4[2]), "r"(l4[3]) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the tensor core
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      mbar_arrive(a_ready(t));
+      mbar_arrive(y_ready(s));
     }
   } else {
     // ------------------------------------------------------------ accumulators
