@@ -55,7 +55,7 @@ PROTOTYPES = {
     "gcs_bn_stats": (c_int32, [P, I64, I64, I32, P, P, P, I64, P]),
     "gcs_bn_fold": (c_int32, [P, P, P, P, F32, F32, P, P, P, P, I32, P]),
     "gcs_bn_prelu_fwd": (c_int32, [P, I64, P, P, P, P, I64, I64, I32, P]),
-    "gcs_bn_prelu_bwd": (c_int32, [P, I64, P, I64, P, P, P, P, P, F32, P, I64, P, P, P, I64, I32, P, I64, P]),
+    "gcs_bn_prelu_bwd": (c_int32, [P, I64, P, I64, P, P, P, P, P, F32, P, I64, P, P, P, P, I64, I32, P, I64, P]),
     "gcs_spmm_rb8_workspace_bytes": (c_int64, [I64]),
     "gcs_spmm_build_rb8": (c_int32, [P, P, I64, I64, P, P, P, I64, P]),
     "gcs_spmm_sum": (c_int32, [P, P, P, P, I64, P, I64, P, P, P, P, I64, I32, P]),

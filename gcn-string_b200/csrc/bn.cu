@@ -289,47 +289,95 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const float* __restrict__ da, int64_t ldda, const float* __restrict__ h, int64_t ldh,
     const float* __restrict__ mean, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ alpha, const float* __restrict__ coef, float* __restrict__ dh, int64_t lddh,
-    int64_t M, int C, int64_t rows_per_split) {
+    int64_t M, int C, int64_t rows_per_split, double* __restrict__ colsum_ws) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + lane) * VEC;
-  if (c >= C) return;
+  const bool valid = c < C;
   const int64_t rb = blockIdx.y * rows_per_split;
   int64_t re = rb + rows_per_split;
   if (re > M) re = M;
-  float mu[VEC], rs[VEC], ga[VEC], be[VEC], al[VEC], c1[VEC], c2[VEC], gr[VEC];
+  // optional: column sums of dh (= the bias gradient of the dense layer in front of this BatchNorm), folded into
+  // this pass instead of a separate read of dh
+  double csum[VEC];
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    mu[k] = __ldg(mean + c + k);
-    ga[k] = __ldg(gamma + c + k);
-    be[k] = __ldg(beta + c + k);
-    al[k] = alpha ? __ldg(alpha + c + k) : 1.f;
-    c1[k] = __ldg(coef + 4 * (c + k));
-    c2[k] = __ldg(coef + 4 * (c + k) + 1);
-    rs[k] = __ldg(coef + 4 * (c + k) + 2);
-    gr[k] = __ldg(coef + 4 * (c + k) + 3);
-  }
-  for (int64_t r = rb + warp; r < re; r += 8) {
-    float hv[VEC], gv[VEC], o[VEC];
-    if (VEC == 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
-      const float4 u = __ldg(reinterpret_cast<const float4*>(da + r * ldda + c));
-      hv[0] = t.x; hv[1] = t.y; hv[2] = t.z; hv[3] = t.w;
-      gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
-    } else {
-      hv[0] = __ldg(h + r * ldh + c);
-      gv[0] = __ldg(da + r * ldda + c);
-    }
+  for (int k = 0; k < VEC; ++k) csum[k] = 0.0;
+  if (valid) {
+    float mu[VEC], rs[VEC], ga[VEC], be[VEC], al[VEC], c1[VEC], c2[VEC], gr[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const float xhat = (hv[k] - mu[k]) * rs[k];
-      const float z = fmaf(ga[k], xhat, be[k]);
-      float dz = gv[k];
-      if (alpha) dz = z > 0.f ? gv[k] : (z < 0.f ? gv[k] * al[k] : 0.f);
-      o[k] = gr[k] * (dz - c1[k] - xhat * c2[k]);
+      mu[k] = __ldg(mean + c + k);
+      ga[k] = __ldg(gamma + c + k);
+      be[k] = __ldg(beta + c + k);
+      al[k] = alpha ? __ldg(alpha + c + k) : 1.f;
+      c1[k] = __ldg(coef + 4 * (c + k));
+      c2[k] = __ldg(coef + 4 * (c + k) + 1);
+      rs[k] = __ldg(coef + 4 * (c + k) + 2);
+      gr[k] = __ldg(coef + 4 * (c + k) + 3);
     }
-    if (VEC == 4) *reinterpret_cast<float4*>(dh + r * lddh + c) = make_float4(o[0], o[1], o[2], o[3]);
-    else dh[r * lddh + c] = o[0];
+    auto out = [&](float hvk, float gvk, int k) {
+      const float xhat = (hvk - mu[k]) * rs[k];
+      const float z = fmaf(ga[k], xhat, be[k]);
+      float dz = gvk;
+      if (alpha) dz = z > 0.f ? gvk : (z < 0.f ? gvk * al[k] : 0.f);
+      return gr[k] * (dz - c1[k] - xhat * c2[k]);
+    };
+    int64_t r = rb + warp;
+    for (; r + 24 < re; r += 32) {                       // four rows per step: eight 128-bit loads in flight
+      float hv[4][VEC], gv[4][VEC], o[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (VEC == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(h + (r + 8 * u) * ldh + c));
+          const float4 g = __ldg(reinterpret_cast<const float4*>(da + (r + 8 * u) * ldda + c));
+          hv[u][0] = t.x; hv[u][1] = t.y; hv[u][2] = t.z; hv[u][3] = t.w;
+          gv[u][0] = g.x; gv[u][1] = g.y; gv[u][2] = g.z; gv[u][3] = g.w;
+        } else {
+          hv[u][0] = __ldg(h + (r + 8 * u) * ldh + c);
+          gv[u][0] = __ldg(da + (r + 8 * u) * ldda + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[u][k] = out(hv[u][k], gv[u][k], k);
+        if (VEC == 4) *reinterpret_cast<float4*>(dh + (r + 8 * u) * lddh + c) = make_float4(o[u][0], o[u][1], o[u][2], o[u][3]);
+        else dh[(r + 8 * u) * lddh + c] = o[u][0];
+      }
+      if (colsum_ws) {                                   // fp32 over the four rows, one fp64 fold
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) csum[k] += static_cast<double>((o[0][k] + o[1][k]) + (o[2][k] + o[3][k]));
+      }
+    }
+    for (; r < re; r += 8) {
+      float hv[VEC], gv[VEC], o[VEC];
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(h + r * ldh + c));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(da + r * ldda + c));
+        hv[0] = t.x; hv[1] = t.y; hv[2] = t.z; hv[3] = t.w;
+        gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
+      } else {
+        hv[0] = __ldg(h + r * ldh + c);
+        gv[0] = __ldg(da + r * ldda + c);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = out(hv[k], gv[k], k);
+      if (VEC == 4) *reinterpret_cast<float4*>(dh + r * lddh + c) = make_float4(o[0], o[1], o[2], o[3]);
+      else dh[r * lddh + c] = o[0];
+      if (colsum_ws) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) csum[k] += static_cast<double>(o[k]);
+      }
+    }
   }
+  if (colsum_ws) block_store_partials<VEC>(csum, colsum_ws + static_cast<int64_t>(blockIdx.y) * C + c, 0, 0, valid);
+}
+
+__global__ void bn_bwd_dbias_final_kernel(const double* __restrict__ ws, int splits, int C, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < splits; ++k) s += ws[static_cast<int64_t>(k) * C + c];
+  dbias[c] = static_cast<float>(s);
 }
 
 }  // namespace gcs
@@ -396,7 +444,8 @@ extern "C" int gcs_bn_prelu_fwd(const float* h, int64_t ldh, const float* scale,
 extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh, const float* mean,
                                 const float* var, const float* gamma, const float* beta, const float* alpha,
                                 float eps, float* dh, int64_t lddh, float* dgamma, float* dbeta, float* dalpha,
-                                int64_t M, int32_t C, void* workspace, int64_t workspace_bytes, gcs_stream stream) {
+                                float* dbias, int64_t M, int32_t C, void* workspace, int64_t workspace_bytes,
+                                gcs_stream stream) {
   GCS_CHECK_ARG(M > 0 && C > 0, "gcs_bn_prelu_bwd: needs at least one row");
   GCS_CHECK_ARG(da && h && mean && var && gamma && beta && dh && workspace, "gcs_bn_prelu_bwd: null pointer");
   GCS_CHECK_ARG(ldda >= C && ldh >= C && lddh >= C, "gcs_bn_prelu_bwd: leading dimension smaller than C");
@@ -417,8 +466,13 @@ extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, i
   GCS_CHECK_LAUNCH("bn_bwd_partial_kernel");
   bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, M, var, gamma, eps, dgamma, dbeta, dalpha, coef);
   GCS_CHECK_LAUNCH("bn_bwd_final_kernel");
-  if (vec) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split);
-  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split);
+  double* cws = dbias ? ws : nullptr;          // the reduction partials are consumed: reuse their space
+  if (vec) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);
+  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);
   GCS_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  if (dbias) {
+    bn_bwd_dbias_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, dbias);
+    GCS_CHECK_LAUNCH("bn_bwd_dbias_final_kernel");
+  }
   return GCS_OK;
 }

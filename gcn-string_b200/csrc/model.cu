@@ -308,9 +308,10 @@ static int block_backward(const gcs_model_config& c, const Plan& p, int bi, cons
   GCS_TIMED("bn_prelu_bwd", gcs_bn_prelu_bwd(da, ldda, h, ldh, mean, var, params + b.gamma(), params + b.beta(),
                                              b.has_alpha ? params + b.alpha() : nullptr, c.bn_epsilon, dh, lddh,
                                              grads + b.gamma(), grads + b.beta(),
-                                             b.has_alpha ? grads + b.alpha() : nullptr, rows, b.m_out, p.bn_ws,
-                                             p.bn_ws_bytes, st));
-  GCS_TIMED("linear_bwd_weight", gcs_linear_bwd_weight(in, ld_in, dh, lddh, grads + b.kernel(), grads + b.bias(), rows,
+                                             b.has_alpha ? grads + b.alpha() : nullptr, grads + b.bias(), rows, b.m_out,
+                                             p.bn_ws, p.bn_ws_bytes, st));
+  // the bias gradient (column sums of dh) came out of the BatchNorm backward's apply pass
+  GCS_TIMED("linear_bwd_weight", gcs_linear_bwd_weight(in, ld_in, dh, lddh, grads + b.kernel(), nullptr, rows,
                                                        b.k_in, b.m_out, p.lw_ws, p.lw_ws_bytes, st));
   if (din)
     GCS_TIMED("linear_bwd_input", gcs_linear_bwd_input(dh, lddh, params + b.kernel(), din, lddin, rows, b.k_in,

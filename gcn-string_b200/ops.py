@@ -221,7 +221,8 @@ def bn_prelu_fwd(h, scale, shift, alpha=None, out=None):
     return out
 
 
-def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3):
+def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3, want_dbias=False):
+    """-> (dh, dgamma, dbeta, dalpha[, dbias]); dbias = column sums of dh (bias gradient of the dense layer in front)."""
     torch = _t()
     lib = _lib.load()
     da, ldda = _mat(da, "da")
@@ -231,11 +232,12 @@ def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3):
     dgamma = torch.empty(c, dtype=torch.float32, device="cuda")
     dbeta = torch.empty(c, dtype=torch.float32, device="cuda")
     dalpha = torch.empty(c, dtype=torch.float32, device="cuda") if alpha is not None else None
+    dbias = torch.empty(c, dtype=torch.float32, device="cuda") if want_dbias else None
     ws = _ws(lib.gcs_bn_workspace_bytes(m, c))
     check(lib.gcs_bn_prelu_bwd(ptr(da), ldda, ptr(h), ldh, ptr(mean), ptr(var), ptr(gamma), ptr(beta), ptr(alpha),
-                               eps, ptr(dh), c, ptr(dgamma), ptr(dbeta), ptr(dalpha), m, c, ptr(ws), ws.numel(),
-                               stream_ptr()), "gcs_bn_prelu_bwd")
-    return dh, dgamma, dbeta, dalpha
+                               eps, ptr(dh), c, ptr(dgamma), ptr(dbeta), ptr(dalpha), ptr(dbias), m, c, ptr(ws),
+                               ws.numel(), stream_ptr()), "gcs_bn_prelu_bwd")
+    return (dh, dgamma, dbeta, dalpha, dbias) if want_dbias else (dh, dgamma, dbeta, dalpha)
 
 
 # ------------------------------------------------------------------ aggregation (K3/K7)

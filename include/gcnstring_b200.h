@@ -115,7 +115,10 @@ int gcs_linear_bwd_input(const float* dH, int64_t ldh, const float* W, float* dA
  *               (inference: pass the moving statistics as mean/var and NULL moving_*)
  *   bn_prelu_fwd: out = prelu(h * scale + shift, alpha)   (alpha NULL -> identity)
  *   bn_prelu_bwd: given da = dLoss/d(out): dgamma, dbeta, dalpha (NULL-able) and
- *               dh = dLoss/dh for training-mode BN.  workspace as bn_stats.
+ *               dh = dLoss/dh for training-mode BN.  dbias (NULL-able) receives the column
+ *               sums of dh, i.e. the bias gradient of the dense layer that produced h, so
+ *               that gcs_linear_bwd_weight can be called with db = NULL (one read of dh
+ *               saved).  workspace as bn_stats.
  * --------------------------------------------------------------------------------- */
 int64_t gcs_bn_workspace_bytes(int64_t M, int32_t C);
 int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, float* mean, float* var,
@@ -129,8 +132,8 @@ int gcs_bn_prelu_fwd(const float* h, int64_t ldh, const float* scale, const floa
 int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh, const float* mean,
                      const float* var, const float* gamma, const float* beta, const float* alpha,
                      float eps, float* dh, int64_t lddh, float* dgamma, float* dbeta,
-                     float* dalpha, int64_t M, int32_t C, void* workspace, int64_t workspace_bytes,
-                     gcs_stream stream);
+                     float* dalpha, float* dbias, int64_t M, int32_t C, void* workspace,
+                     int64_t workspace_bytes, gcs_stream stream);
 
 /* ---------------------------------------------------------------------------------
  * K3/K7  Sum aggregation  Y = pattern(A) . f(X)   (MessagePassing.propagate: tf.gather +

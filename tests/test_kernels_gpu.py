@@ -189,6 +189,12 @@ def test_batchnorm_prelu_forward_backward(M, C):
     assert rel_err(host(dgamma), dg_r) < 5 * TOL and rel_err(host(dbeta), db_r) < 5 * TOL
     assert rel_err(host(dalpha), (da * np.minimum(z, 0)).sum(0)) < TOL
     assert rel_err(np.where(near_kink, 0, host(dh)), np.where(near_kink, 0, dh_r)) < 5 * TOL
+    # the fused bias gradient: column sums of the dh the kernel wrote (mathematically zero after BatchNorm;
+    # the check is against the fp64 sum of the kernel's own fp32 dh, on the scale of sum |dh|)
+    dh2, _, _, _, dbias = ops.bn_prelu_bwd(dev(da), dev(h), mean, var, dev(gamma), dev(beta), dev(alpha), want_dbias=True)
+    assert torch.equal(dh2, dh)
+    want = host(dh).astype(np.float64).sum(0)
+    assert np.abs(host(dbias) - want).max() <= 1e-6 * np.abs(host(dh)).sum(0).max()
 
 
 # ---------------------------------------------------------------- K3/K7 aggregation
