@@ -897,6 +897,8 @@ int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpos
 
 int64_t split_workspace_bytes(int K, int N) { return round_up(2LL * K * N * sizeof(float), 256); }
 
+static int g_max_chain_k = 512;                          // longest tensor-core accumulation chain of the forward / dX kernel
+void set_max_chain_k(int k) { if (k >= BK && k % BK == 0) g_max_chain_k = k; }
 static int g_pair_mode = 1;                               // 1 = CTA-pair kernel (default), 0 = single-CTA kernel
 void set_pair_mode(int m) { g_pair_mode = m; }
 
@@ -905,10 +907,7 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
            int64_t M, int K, int N, int accumulate, cudaStream_t st, const float* rowbias, int64_t ld_rowbias,
            const int64_t* seg) {
   alignas(64) CUtensorMap ma, mh, ml, mc;
-  GCS_TRY(make_map(&ma, A, M, K, lda, BM));
   if (g_pair_mode && ceil_div(M, 2 * BM) * (N / BN) < (1LL << 30)) {
-    GCS_TRY(make_map(&mh, Bt_hi, N, K, K, 64));
-    GCS_TRY(make_map(&ml, Bt_lo, N, K, K, 64));
     GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));        // output boxes of 32 rows x 32 columns (128 B rows, SWIZZLE_128B)
     static bool attr2 = false;
     if (!attr2) {
@@ -919,11 +918,26 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
     const int num_tiles = static_cast<int>(ceil_div(M, 2 * BM)) * n_tiles;
     const int pairs = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;      // persistent: one CTA pair per SM pair
     dim3 grid(2, pairs);                                                           // x = rank in the pair
-    linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, bias, M, K, n_tiles, num_tiles, accumulate,
-                                                               rowbias, ld_rowbias, seg);
-    GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
+    // The tensor core adds every K = 8 step into the fp32 accumulator with TRUNCATION: a chain of n steps shrinks the
+    // result by ~n * 2^-26 (measured 2e-5 on the BatchNorm variances of a hidden-512 model with K = 2048 in one chain;
+    // with chains of 1024 one gradient tensor of that model was 1.4e-5 off the float64 oracle, with 512 all are inside
+    // max(1e-5, 4 x the error of a float32 CPU run)).  Longer reductions therefore run as chunks of <= 512 (64 steps)
+    // that meet in C through the epilogue's round-to-nearest reduce-add: +3% on the hidden-512 step.
+    const int kMaxChainK = g_max_chain_k;
+    for (int k0 = 0; k0 < K; k0 += kMaxChainK) {
+      const int kc = K - k0 < kMaxChainK ? K - k0 : kMaxChainK;
+      GCS_TRY(make_map(&ma, A + k0, M, kc, lda, BM));
+      GCS_TRY(make_map(&mh, Bt_hi + k0, N, kc, K, 64));
+      GCS_TRY(make_map(&ml, Bt_lo + k0, N, kc, K, 64));
+      const bool first = k0 == 0;
+      linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
+                                                                 first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
+                                                                 seg);
+      GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
+    }
     return GCS_OK;
   }
+  GCS_TRY(make_map(&ma, A, M, K, lda, BM));
   GCS_TRY(make_map(&mh, Bt_hi, N, K, K, BN));
   GCS_TRY(make_map(&ml, Bt_lo, N, K, K, BN));
   static bool attr = false;

@@ -344,3 +344,32 @@ def test_evaluate_pass_matches_oracle_and_sklearn(small_case):
     f0, t0, _ = skm.roc_curve(labels, host(scores).astype(np.float64))
     assert np.allclose(fpr, f0) and np.allclose(tpr, t0)
     assert abs(roc_auc(labels, scores) - skm.roc_auc_score(labels, host(scores).astype(np.float64))) < 1e-9
+
+
+def test_forward_backward_hidden512_cfg5_shape():
+    """BASELINE cfg5 shape at reduced size: large inter-protein graphs (deg ~32) with hidden 512 -
+    the concat width reaches 2560 and every dense transform runs on the tcgen05 path with
+    N = 512 (four 128-column tiles per row pair) and K up to 2048.  alpha = 1 (no PReLU kink,
+    see the cfg1 test) so that gradients can be held to 1e-5."""
+    ds = synthetic.make_dataset(3, seed=5, n_mean=1200, deg=32, n_feat=32)
+    graphs = [ds.graph(k) for k in range(3)]
+    (xr, (idx, _, _), seg), yr = batching_ref.collate(graphs)
+    cfg = GNNConfig(in_features=32, output=2, activation="softmax", hidden=512)
+    w, s = g.init_params(cfg, seed=6, perturb=True)
+    for b in block_specs(cfg):
+        o, n = b.alpha
+        w[o:o + n] = 1.0
+    ref = O1.loss_and_grads(cfg, block_specs(cfg), w, s, xr, idx[:, 0], idx[:, 1], seg, yr, 3)
+    loader = g.DisjointLoader(ds, batch_size=3, epochs=1, shuffle=False)
+    (x, a, i), y = next(loader)
+    assert a.nnz / a.n_rows > 25
+    model = make_model(cfg, w, s)
+    loss_acc, probs = model.train_step_grads([x, a, i], y)
+    assert abs(host(loss_acc)[0] - ref["loss"]) < TOL * abs(ref["loss"])
+    assert rel_err(host(probs), ref["probs"]) < TOL
+    assert rel_err(host(model.state), ref["new_state"]) < TOL
+    o2 = O2.loss_and_grads(cfg, block_specs(cfg), w, s, xr, idx[:, 0], idx[:, 1], seg, yr, 3)
+    assert_grads_close(host(model.grads), ref["grads"], cfg, o2["grads"])
+    p_inf = model([x, a, i], training=False)
+    ref_inf, _ = O1.forward(cfg, block_specs(cfg), w, s, xr, idx[:, 0], idx[:, 1], seg, 3, training=False)
+    assert rel_err(host(p_inf), ref_inf) < TOL
