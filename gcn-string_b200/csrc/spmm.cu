@@ -70,8 +70,11 @@ __global__ void __launch_bounds__(128) rb8_build_kernel(const int32_t* __restric
 
 // One row block per `lanes` threads (lanes = H/4, each lane owns 4 columns); a CTA walks a contiguous
 // range of row blocks so that neighbouring blocks reuse each other's X rows through L1.
+// Occupancy: the prologue-free instance fits 64 registers -> four CTAs per SM (measured 277 us vs 335 us with three:
+// the gather chain is latency-bound); the instance with the prologue needs 77 registers and loses more from a 64-register
+// cap (411 us) or a two-deep unroll (378 us) than it gains from the fourth CTA (356 us with three).
 template <bool kTransform>
-__global__ void __launch_bounds__(256) spmm_rb8_kernel(
+__global__ void __launch_bounds__(256, kTransform ? 3 : 4) spmm_rb8_kernel(
     const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent, int n_rows, int n_blocks,
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ alpha, float* __restrict__ Y, int64_t ldy, int lanes, int slots, int iters) {
@@ -205,7 +208,7 @@ struct SpmmArgs {
 };
 
 int g_rows_iters = 16;   // tuning knob (gcs_debug_set_param 1)
-int g_rb8_iters = 4;     // row blocks per slot per CTA (gcs_debug_set_param 2)
+int g_rb8_iters = 2;     // row blocks per slot per CTA (gcs_debug_set_param 2); sweep 1/2/3/4: 372/356/358/367 us fwd, 283/277/287/297 us bwd
 
 template <int VEC>
 int launch_rows(const SpmmArgs& a) {
@@ -294,9 +297,9 @@ extern "C" int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const 
   SpmmArgs a{rowptr, colidx, rb8_blk_ptr, rb8_ent, n_rows, X, ldx, scale, shift, alpha, Y, ldy, H, as_stream(stream)};
   const bool vec_ok = (H % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
                       (!scale || (aligned16(scale) && aligned16(shift) && aligned16(alpha)));
-  // RB8 pays off when the BN+PReLU prologue is fused (one transform per block instead of per row:
-  // 367 vs 463 us at cfg2); the plain gather of the backward is faster row by row (316 vs 342 us).
-  const bool want_rb8 = g_spmm_mode == 2 || (g_spmm_mode == 0 && scale != nullptr);
+  // RB8 whenever the structure is supplied: with the BN+PReLU prologue one transform per block instead of per row
+  // (356 vs 463 us at cfg2), and for the plain gather of the backward 277 vs 319 us row by row.
+  const bool want_rb8 = g_spmm_mode != 1;
   if (want_rb8 && rb8_blk_ptr && vec_ok && H / 4 <= 256 && 256 % (H / 4) == 0) return launch_rb8(a);
   if (vec_ok) return launch_rows<4>(a);
   return launch_rows<1>(a);

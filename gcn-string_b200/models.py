@@ -218,7 +218,7 @@ class GeneralGNN:
         rp_t, ci_t = a.transposed() if need_transpose else (None, None)
         use_rb8 = self.use_rb8 and x.shape[0] < (1 << 24) and self.cfg.hidden % 4 == 0
         rb8 = a.rb8 if use_rb8 else (None, None)
-        rb8_t = (None, None)     # the prologue-free backward gather is faster on the plain CSR kernel
+        rb8_t = a.rb8_t if (use_rb8 and need_transpose) else (None, None)   # the same arrays when the pattern is symmetric
         batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, 0, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
                            ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None,
                            ptr(seg), ptr(rb8[0]), ptr(rb8[1]), ptr(rb8_t[0]), ptr(rb8_t[1]))
