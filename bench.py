@@ -55,7 +55,7 @@ def _peaks():
 def _ncu_traffic():
     """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (or None)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_spmm_rb8_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_spmm_rb4_ncu.json")) as f:
             d = json.load(f)
         return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
     except Exception:
@@ -254,7 +254,7 @@ def run_b200(args):
         roofline = {"kernel": "spmm_graph_kernel (K3, GeneralConv aggregation fwd, BN+PReLU fused on load)",
                     "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": _ncu_traffic(),
-                    "traffic_source": "profiles/r01_spmm_rb8_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                    "traffic_source": "profiles/r01_spmm_rb4_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": t * 1e6,
                     "edges_per_sec": nnz / t, "frac_of_nominal_8TBs": ach / 8000.0}
     # the time-dominant kernels are the dense transforms (3xTF32 on tcgen05): fp32-equivalent rate of the forward GEMMs

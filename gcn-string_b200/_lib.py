@@ -29,7 +29,7 @@ class Batch(Structure):
     _fields_ = [("n_nodes", c_int64), ("nnz", c_int64), ("n_graphs", c_int32), ("reserved", c_int32),
                 ("rowptr", c_void_p), ("colidx", c_void_p), ("rowptr_t", c_void_p), ("colidx_t", c_void_p),
                 ("graph_ptr", c_void_p), ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p),
-                ("seg_ids", c_void_p), ("rb8_blk_ptr", c_void_p), ("rb8_ent", c_void_p), ("rb8_blk_ptr_t", c_void_p), ("rb8_ent_t", c_void_p)]
+                ("seg_ids", c_void_p), ("rb4_blk_ptr", c_void_p), ("rb4_ent", c_void_p), ("rb4_blk_ptr_t", c_void_p), ("rb4_ent_t", c_void_p)]
 
 
 P = c_void_p
@@ -56,8 +56,8 @@ PROTOTYPES = {
     "gcs_bn_fold": (c_int32, [P, P, P, P, F32, F32, P, P, P, P, I32, P]),
     "gcs_bn_prelu_fwd": (c_int32, [P, I64, P, P, P, P, I64, I64, I32, P]),
     "gcs_bn_prelu_bwd": (c_int32, [P, I64, P, I64, P, P, P, P, P, F32, P, I64, P, P, P, P, I64, I32, P, I64, P]),
-    "gcs_spmm_rb8_workspace_bytes": (c_int64, [I64]),
-    "gcs_spmm_build_rb8": (c_int32, [P, P, I64, I64, P, P, P, I64, P]),
+    "gcs_spmm_rb4_workspace_bytes": (c_int64, [I64]),
+    "gcs_spmm_build_rb4": (c_int32, [P, P, I64, I64, P, P, P, I64, P]),
     "gcs_spmm_sum": (c_int32, [P, P, P, P, I64, P, I64, P, P, P, P, I64, I32, P]),
     "gcs_segment_sum_fwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_segment_sum_bwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),

@@ -264,7 +264,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
     const float* scale = p.stat[bi] + 2 * H;
-    GCS_TIMED("spmm_fwd", gcs_spmm_sum(bt.rowptr, bt.colidx, bt.rb8_blk_ptr, bt.rb8_ent, N,
+    GCS_TIMED("spmm_fwd", gcs_spmm_sum(bt.rowptr, bt.colidx, bt.rb4_blk_ptr, bt.rb4_ent, N,
                                        p.h[bi], H, scale, scale + H, params + b.alpha(),
                                        p.cat + static_cast<int64_t>(L - k - 1) * H, Wc, H, st));
   }
@@ -378,7 +378,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
       dz = blk;
       lddz = Wc;
     }
-    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb8_blk_ptr_t, bt.rb8_ent_t, N, dz, lddz, nullptr, nullptr,
+    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb4_blk_ptr_t, bt.rb4_ent_t, N, dz, lddz, nullptr, nullptr,
                                        nullptr, p.tmp_a, H, H, st));
     GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N, p.cat + static_cast<int64_t>(L - k) * H, Wc,
                            p.dhcat + static_cast<int64_t>(k) * H, ldd, nullptr, 0, 0, st));

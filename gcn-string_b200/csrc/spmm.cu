@@ -10,10 +10,10 @@
 // ascending column order — no atomics, no cross-lane reduction.
 //
 // Two kernels:
-//  * spmm_rb8_kernel  — consumes the RB8 row-block format (built once per batch from the CSR by
-//    gcs_spmm_build_rb8); H/4 lanes per block of 8 output rows, 128-bit gathers from global memory
+//  * spmm_rb4_kernel  — consumes the RB4 row-block format (built once per batch from the CSR by
+//    gcs_spmm_build_rb4); H/4 lanes per block of 4 output rows, 128-bit gathers from global memory
 //    (L1/L2 serve the re-reads), 4 union entries in flight per lane.
-//  * spmm_rows_kernel — plain CSR, H/4 lanes per row; used when no RB8 structure is supplied or the
+//  * spmm_rows_kernel — plain CSR, H/4 lanes per row; used when no RB4 structure is supplied or the
 //    rows do not share neighbours, and (VEC = 1) for odd widths / unaligned views.
 // A shared-memory-staged tile design (per-graph slabs, ghost rows) was built and measured first; it
 // loses to both (profiles/r01_spmm_*.md): its four dependent staging phases leave the SM idle and
@@ -23,17 +23,21 @@
 namespace gcs {
 
 // ---------------------------------------------------------------------------------------------
-// RB8: row-block-of-8 format.  Residue contact maps are banded, so 8 consecutive rows share most of
-// their neighbours.  For each block of 8 rows the sorted UNION of its column indices is stored once,
-// each entry with an 8-bit mask of the rows that contain it: ent = (col << 8) | mask.  A neighbour
-// row of X is then loaded (and BN+PReLU-transformed) once per block instead of once per row — 2.4x
-// fewer gathers and transforms on E. coli-shaped graphs — while every output row still adds its own
+// RB4: row-block-of-4 format.  Residue contact maps are banded, so consecutive rows share most of
+// their neighbours.  For each block of 4 rows the sorted UNION of its column indices is stored once,
+// each entry with a mask of the rows that contain it: ent = (col << 8) | mask.  A neighbour row of X
+// is then loaded (and BN+PReLU-transformed) once per block instead of once per row - 2.1x fewer
+// gathers and transforms on E. coli-shaped graphs - while every output row still adds its own
 // neighbours in ascending column order (bit-identical to the CSR kernels).
-constexpr int kRB = 8;
+// Block height, measured on B200 at cfg2 (forward with prologue / plain gather of the backward):
+//   8 rows: union 2.6x smaller, 32 predicated add slots per entry, 77 / 61 registers   356 / 277 us
+//   4 rows: union 2.1x smaller, 16 slots per entry, 56 / 47 registers, 4 CTAs per SM    334 / 262 us
+//   2 rows: union 1.5x smaller                                                          399 / 272 us
+constexpr int kRB = 4;
 
-// 8-way merge of the sorted neighbour lists of one row block; kFill = false counts the union size.
+// kRB-way merge of the sorted neighbour lists of one row block; kFill = false counts the union size.
 template <bool kFill>
-__global__ void __launch_bounds__(128) rb8_build_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+__global__ void __launch_bounds__(128) rb4_build_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                                         int n_rows, int n_blocks, const int32_t* __restrict__ blk_ptr,
                                                         int32_t* __restrict__ count, uint32_t* __restrict__ ent) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,11 +74,8 @@ __global__ void __launch_bounds__(128) rb8_build_kernel(const int32_t* __restric
 
 // One row block per `lanes` threads (lanes = H/4, each lane owns 4 columns); a CTA walks a contiguous
 // range of row blocks so that neighbouring blocks reuse each other's X rows through L1.
-// Occupancy: the prologue-free instance fits 64 registers -> four CTAs per SM (measured 277 us vs 335 us with three:
-// the gather chain is latency-bound); the instance with the prologue needs 77 registers and loses more from a 64-register
-// cap (411 us) or a two-deep unroll (378 us) than it gains from the fourth CTA (356 us with three).
 template <bool kTransform>
-__global__ void __launch_bounds__(256, kTransform ? 3 : 4) spmm_rb8_kernel(
+__global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
     const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent, int n_rows, int n_blocks,
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ alpha, float* __restrict__ Y, int64_t ldy, int lanes, int slots, int iters) {
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(256, kTransform ? 3 : 4) spmm_rb8_kernel(
     float4 acc[kRB];
 #pragma unroll
     for (int r = 0; r < kRB; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // Predicated adds: 32 issue slots per entry of which ~10 do work.  Measured alternatives on
-    // B200: warp-uniform branches per row / per half block 427 us, packed add.f32x2 434 us, this 367 us.
+    // Predicated adds: 4 * kRB issue slots per entry of which about a third do work.  Measured alternatives on B200
+    // (8-row blocks): warp-uniform branches per row / per half block 427 us, packed add.f32x2 434 us, predicated 367 us.
     auto scatter = [&](const float4& v, uint32_t m) {
 #pragma unroll
       for (int r = 0; r < kRB; ++r) {
@@ -208,7 +209,7 @@ struct SpmmArgs {
 };
 
 int g_rows_iters = 16;   // tuning knob (gcs_debug_set_param 1)
-int g_rb8_iters = 2;     // row blocks per slot per CTA (gcs_debug_set_param 2); sweep 1/2/3/4: 372/356/358/367 us fwd, 283/277/287/297 us bwd
+int g_rb4_iters = 2;     // row blocks per slot per CTA (gcs_debug_set_param 2); sweep on 8-row blocks 1/2/3/4: 372/356/358/367 us fwd, 283/277/287/297 us bwd; on 4-row blocks 2/4/8: 338/334/349, 262/264/293
 
 template <int VEC>
 int launch_rows(const SpmmArgs& a) {
@@ -225,21 +226,21 @@ int launch_rows(const SpmmArgs& a) {
   return GCS_OK;
 }
 
-int launch_rb8(const SpmmArgs& a) {
+int launch_rb4(const SpmmArgs& a) {
   const int lanes = a.H / 4;
   const int slots = 256 / lanes;
   const int n_blocks = static_cast<int>(ceil_div(a.n_rows, kRB));
-  const int iters = g_rb8_iters;
+  const int iters = g_rb4_iters;
   dim3 grid(static_cast<unsigned>(ceil_div(n_blocks, static_cast<int64_t>(slots) * iters)));
   if (a.scale)
-    spmm_rb8_kernel<true><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, lanes, slots, iters);
+    spmm_rb4_kernel<true><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, lanes, slots, iters);
   else
-    spmm_rb8_kernel<false><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, lanes, slots, iters);
-  GCS_CHECK_LAUNCH("spmm_rb8_kernel");
+    spmm_rb4_kernel<false><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, lanes, slots, iters);
+  GCS_CHECK_LAUNCH("spmm_rb4_kernel");
   return GCS_OK;
 }
 
-int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB8 whenever supplied
+int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 whenever supplied
 
 }  // namespace
 
@@ -248,24 +249,24 @@ extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
 namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_pair_mode(int m); void set_max_chain_k(int k); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
-  if (id == 2 && value > 0) g_rb8_iters = value;
+  if (id == 2 && value > 0) g_rb4_iters = value;
   if (id == 3) gcs::tc::set_wgrad_chain(value);
   if (id == 4) gcs::tc::set_pair_mode(value);
   if (id == 5) gcs::tc::set_max_chain_k(value);
 }
 
-extern "C" int64_t gcs_spmm_rb8_workspace_bytes(int64_t n_rows) {
+extern "C" int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows) {
   return round_up((ceil_div(n_rows > 0 ? n_rows : 1, kRB) + 1) * static_cast<int64_t>(sizeof(int32_t)), 256);
 }
 
-extern "C" int gcs_spmm_build_rb8(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
+extern "C" int gcs_spmm_build_rb4(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
                                   int32_t* blk_ptr, uint32_t* ent, void* workspace, int64_t workspace_bytes,
                                   gcs_stream stream) {
-  GCS_CHECK_ARG(rowptr && blk_ptr && workspace && n_rows >= 0 && nnz >= 0, "gcs_spmm_build_rb8: bad argument");
-  GCS_CHECK_ARG(nnz == 0 || (colidx && ent), "gcs_spmm_build_rb8: null column / entry array");
-  GCS_CHECK_ARG(n_rows < (1 << 24), "gcs_spmm_build_rb8: RB8 packs the column index in 24 bits (n_rows < 16 777 216)");
-  if (workspace_bytes < gcs_spmm_rb8_workspace_bytes(n_rows))
-    return fail(GCS_ERR_WORKSPACE, "gcs_spmm_build_rb8: workspace too small");
+  GCS_CHECK_ARG(rowptr && blk_ptr && workspace && n_rows >= 0 && nnz >= 0, "gcs_spmm_build_rb4: bad argument");
+  GCS_CHECK_ARG(nnz == 0 || (colidx && ent), "gcs_spmm_build_rb4: null column / entry array");
+  GCS_CHECK_ARG(n_rows < (1 << 24), "gcs_spmm_build_rb4: RB4 packs the column index in 24 bits (n_rows < 16 777 216)");
+  if (workspace_bytes < gcs_spmm_rb4_workspace_bytes(n_rows))
+    return fail(GCS_ERR_WORKSPACE, "gcs_spmm_build_rb4: workspace too small");
   cudaStream_t st = as_stream(stream);
   const int nb = static_cast<int>(ceil_div(n_rows, kRB));
   int32_t* cnt = static_cast<int32_t*>(workspace);
@@ -273,16 +274,16 @@ extern "C" int gcs_spmm_build_rb8(const int32_t* rowptr, const int32_t* colidx, 
     GCS_CUDA(cudaMemsetAsync(blk_ptr, 0, sizeof(int32_t), st));
     return GCS_OK;
   }
-  rb8_build_kernel<false><<<static_cast<unsigned>(ceil_div(nb, 128)), 128, 0, st>>>(rowptr, colidx, static_cast<int>(n_rows), nb, nullptr, cnt, nullptr);
-  GCS_CHECK_LAUNCH("rb8_build_kernel<count>");
+  rb4_build_kernel<false><<<static_cast<unsigned>(ceil_div(nb, 128)), 128, 0, st>>>(rowptr, colidx, static_cast<int>(n_rows), nb, nullptr, cnt, nullptr);
+  GCS_CHECK_LAUNCH("rb4_build_kernel<count>");
   GCS_TRY(exclusive_scan_i32(cnt, nb, blk_ptr, st));
-  rb8_build_kernel<true><<<static_cast<unsigned>(ceil_div(nb, 128)), 128, 0, st>>>(rowptr, colidx, static_cast<int>(n_rows), nb, blk_ptr, nullptr, ent);
-  GCS_CHECK_LAUNCH("rb8_build_kernel<fill>");
+  rb4_build_kernel<true><<<static_cast<unsigned>(ceil_div(nb, 128)), 128, 0, st>>>(rowptr, colidx, static_cast<int>(n_rows), nb, blk_ptr, nullptr, ent);
+  GCS_CHECK_LAUNCH("rb4_build_kernel<fill>");
   return GCS_OK;
 }
 
-extern "C" int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb8_blk_ptr,
-                            const uint32_t* rb8_ent, int64_t n_rows, const float* X, int64_t ldx,
+extern "C" int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb4_blk_ptr,
+                            const uint32_t* rb4_ent, int64_t n_rows, const float* X, int64_t ldx,
                             const float* scale, const float* shift, const float* alpha, float* Y,
                             int64_t ldy, int32_t H, gcs_stream stream) {
   GCS_CHECK_ARG(n_rows >= 0 && H > 0, "gcs_spmm_sum: bad size (n_rows=%lld, H=%d)", (long long)n_rows, H);
@@ -291,16 +292,16 @@ extern "C" int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const 
   GCS_CHECK_ARG(ldx >= H && ldy >= H, "gcs_spmm_sum: leading dimension smaller than H");
   GCS_CHECK_ARG((scale != nullptr) == (shift != nullptr) && (scale != nullptr) == (alpha != nullptr),
                 "gcs_spmm_sum: scale/shift/alpha must be all NULL or all set");
-  GCS_CHECK_ARG((rb8_blk_ptr != nullptr) == (rb8_ent != nullptr), "gcs_spmm_sum: rb8_blk_ptr and rb8_ent go together");
+  GCS_CHECK_ARG((rb4_blk_ptr != nullptr) == (rb4_ent != nullptr), "gcs_spmm_sum: rb4_blk_ptr and rb4_ent go together");
   GCS_CHECK_ARG(X != Y, "gcs_spmm_sum: in-place aggregation is not defined");
   GCS_CHECK_ARG(n_rows < INT32_MAX, "gcs_spmm_sum: n_rows exceeds int32 CSR range");
-  SpmmArgs a{rowptr, colidx, rb8_blk_ptr, rb8_ent, n_rows, X, ldx, scale, shift, alpha, Y, ldy, H, as_stream(stream)};
+  SpmmArgs a{rowptr, colidx, rb4_blk_ptr, rb4_ent, n_rows, X, ldx, scale, shift, alpha, Y, ldy, H, as_stream(stream)};
   const bool vec_ok = (H % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
                       (!scale || (aligned16(scale) && aligned16(shift) && aligned16(alpha)));
-  // RB8 whenever the structure is supplied: with the BN+PReLU prologue one transform per block instead of per row
-  // (356 vs 463 us at cfg2), and for the plain gather of the backward 277 vs 319 us row by row.
-  const bool want_rb8 = g_spmm_mode != 1;
-  if (want_rb8 && rb8_blk_ptr && vec_ok && H / 4 <= 256 && 256 % (H / 4) == 0) return launch_rb8(a);
+  // RB4 whenever the structure is supplied: with the BN+PReLU prologue one transform per block instead of per row
+  // (334 vs 463 us at cfg2), and for the plain gather of the backward 262 vs 319 us row by row.
+  const bool want_rb4 = g_spmm_mode != 1;
+  if (want_rb4 && rb4_blk_ptr && vec_ok && H / 4 <= 256 && 256 % (H / 4) == 0) return launch_rb4(a);
   if (vec_ok) return launch_rows<4>(a);
   return launch_rows<1>(a);
 }

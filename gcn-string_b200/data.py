@@ -121,8 +121,8 @@ class SparseAdjacency:
         self._indices = indices
         self._symmetric = symmetric
         self._t = None
-        self._rb8 = None
-        self._rb8_t = None
+        self._rb4 = None
+        self._rb4_t = None
 
     @classmethod
     def from_indices(cls, indices, dense_shape, values=None):
@@ -168,18 +168,18 @@ class SparseAdjacency:
         return self._symmetric
 
     @property
-    def rb8(self):
-        """(blk_ptr, ent): RB8 row-block form of the pattern for the aggregation kernel."""
-        if self._rb8 is None:
-            self._rb8 = ops.build_rb8(self.rowptr, self.colidx)
-        return self._rb8
+    def rb4(self):
+        """(blk_ptr, ent): RB4 row-block form of the pattern for the aggregation kernel."""
+        if self._rb4 is None:
+            self._rb4 = ops.build_rb4(self.rowptr, self.colidx)
+        return self._rb4
 
     @property
-    def rb8_t(self):
-        """RB8 form of the transposed pattern (the same arrays when symmetric)."""
-        if self._rb8_t is None:
-            self._rb8_t = self.rb8 if self.symmetric else ops.build_rb8(*self.transposed())
-        return self._rb8_t
+    def rb4_t(self):
+        """RB4 form of the transposed pattern (the same arrays when symmetric)."""
+        if self._rb4_t is None:
+            self._rb4_t = self.rb4 if self.symmetric else ops.build_rb4(*self.transposed())
+        return self._rb4_t
 
     def transposed(self):
         """(rowptr_t, colidx_t) of pattern(A)^T; the same arrays when symmetric."""

@@ -82,7 +82,7 @@ class GeneralConv:
         h = self.block.linear(x)
         scale, shift = self.block.fold(h, training)
         alpha = self.block.alpha if self.block.alpha is not None else torch.ones_like(scale)
-        return ops.spmm_sum(a.rowptr, a.colidx, h, scale, shift, alpha, rb8=a.rb8)
+        return ops.spmm_sum(a.rowptr, a.colidx, h, scale, shift, alpha, rb4=a.rb4)
 
 
 class GlobalSumPool:

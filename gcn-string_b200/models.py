@@ -103,7 +103,7 @@ class GeneralGNN:
         self.losses: List = []          # no regularisers (gcn.py:335 adds sum(model.losses) == 0)
         self.cfg: Optional[GNNConfig] = None
         self._ws = None
-        self.use_rb8 = True      # row-block (RB8) aggregation format, built once per batch
+        self.use_rb4 = True      # row-block (RB4) aggregation format, built once per batch
 
     # ------------------------------------------------------------------ build / parameters
     def build(self, in_features: int):
@@ -216,13 +216,13 @@ class GeneralGNN:
         elif a.graph_ptr is not None:
             graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
         rp_t, ci_t = a.transposed() if need_transpose else (None, None)
-        use_rb8 = self.use_rb8 and x.shape[0] < (1 << 24) and self.cfg.hidden % 4 == 0
-        rb8 = a.rb8 if use_rb8 else (None, None)
-        rb8_t = a.rb8_t if (use_rb8 and need_transpose) else (None, None)   # the same arrays when the pattern is symmetric
+        use_rb4 = self.use_rb4 and x.shape[0] < (1 << 24) and self.cfg.hidden % 4 == 0
+        rb4 = a.rb4 if use_rb4 else (None, None)
+        rb4_t = a.rb4_t if (use_rb4 and need_transpose) else (None, None)   # the same arrays when the pattern is symmetric
         batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, 0, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
                            ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None,
-                           ptr(seg), ptr(rb8[0]), ptr(rb8[1]), ptr(rb8_t[0]), ptr(rb8_t[1]))
-        keep = (x, a, graph_ptr, rp_t, ci_t, rb8, rb8_t, seg)   # keep device buffers alive
+                           ptr(seg), ptr(rb4[0]), ptr(rb4[1]), ptr(rb4_t[0]), ptr(rb4_t[1]))
+        keep = (x, a, graph_ptr, rp_t, ci_t, rb4, rb4_t, seg)   # keep device buffers alive
         return batch, keep
 
     def _workspace(self, batch, training):

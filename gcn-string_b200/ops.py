@@ -241,23 +241,23 @@ def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3, want_dbias
 
 
 # ------------------------------------------------------------------ aggregation (K3/K7)
-def build_rb8(rowptr, colidx):
-    """RB8 row-block format of a CSR pattern -> (blk_ptr int32 [ceil(n/8)+1], ent uint32-as-int32 [nnz])."""
+def build_rb4(rowptr, colidx):
+    """RB4 row-block format of a CSR pattern -> (blk_ptr int32 [ceil(n/4)+1], ent uint32-as-int32 [nnz])."""
     torch = _t()
     lib = _lib.load()
     n = rowptr.shape[0] - 1
     nnz = colidx.shape[0]
-    blk_ptr = torch.empty((n + 7) // 8 + 1, dtype=torch.int32, device="cuda")
+    blk_ptr = torch.empty((n + 3) // 4 + 1, dtype=torch.int32, device="cuda")
     ent = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
-    ws = _ws(lib.gcs_spmm_rb8_workspace_bytes(n))
-    check(lib.gcs_spmm_build_rb8(ptr(rowptr), ptr(colidx), n, nnz, ptr(blk_ptr), ptr(ent), ptr(ws), ws.numel(),
-                                 stream_ptr()), "gcs_spmm_build_rb8")
+    ws = _ws(lib.gcs_spmm_rb4_workspace_bytes(n))
+    check(lib.gcs_spmm_build_rb4(ptr(rowptr), ptr(colidx), n, nnz, ptr(blk_ptr), ptr(ent), ptr(ws), ws.numel(),
+                                 stream_ptr()), "gcs_spmm_build_rb4")
     return blk_ptr, ent
 
 
-def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, rb8=None):
+def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, rb4=None):
     """Y = pattern(A) . prelu(x*scale + shift, alpha)  (identity prologue when scale is None).
-    ``rb8`` = (blk_ptr, ent) from ``build_rb8`` selects the row-block kernel (same results)."""
+    ``rb4`` = (blk_ptr, ent) from ``build_rb4`` selects the row-block kernel (same results)."""
     torch = _t()
     lib = _lib.load()
     x, ldx = _mat(x, "x")
@@ -267,7 +267,7 @@ def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, rb
     if out is None:
         out = torch.empty(n, hdim, dtype=torch.float32, device="cuda")
     out, ldy = _mat(out, "y")
-    bp, en = rb8 if rb8 is not None else (None, None)
+    bp, en = rb4 if rb4 is not None else (None, None)
     check(lib.gcs_spmm_sum(ptr(rowptr), ptr(colidx), ptr(bp), ptr(en), n, ptr(x), ldx, ptr(scale), ptr(shift),
                            ptr(alpha), ptr(out), ldy, hdim, stream_ptr()), "gcs_spmm_sum")
     return out

@@ -142,20 +142,20 @@ int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh,
  * pass scale = shift = alpha = NULL for f = identity (that is also the backward:
  * dX = pattern(A)^T . dY, called with the transposed CSR).  Neighbours are accumulated in
  * ascending column order per output row.
- * RB8 (optional): gcs_spmm_build_rb8 derives, once per batch, the row-block-of-8 format from
- * the CSR: per block of 8 consecutive rows the sorted union of their columns, each entry
+ * RB4 (optional): gcs_spmm_build_rb4 derives, once per batch, the row-block-of-4 format from
+ * the CSR: per block of 4 consecutive rows the sorted union of their columns, each entry
  * (col << 8) | mask-of-rows.  Banded residue graphs share most neighbours between consecutive
  * rows, so a neighbour row is gathered and transformed once per block instead of once per row.
- * rb8_blk_ptr needs ceil(n_rows/8)+1 int32, rb8_ent nnz uint32 (upper bound), workspace
- * gcs_spmm_rb8_workspace_bytes(n_rows); n_rows < 2^24.  With rb8_* == NULL the CSR row kernel
+ * rb4_blk_ptr needs ceil(n_rows/4)+1 int32, rb4_ent nnz uint32 (upper bound), workspace
+ * gcs_spmm_rb4_workspace_bytes(n_rows); n_rows < 2^24.  With rb4_* == NULL the CSR row kernel
  * runs; results are bit-identical.  Any matrix structure is accepted either way.
  * --------------------------------------------------------------------------------- */
-int64_t gcs_spmm_rb8_workspace_bytes(int64_t n_rows);
-int gcs_spmm_build_rb8(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
-                       int32_t* rb8_blk_ptr, uint32_t* rb8_ent, void* workspace, int64_t workspace_bytes,
+int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows);
+int gcs_spmm_build_rb4(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
+                       int32_t* rb4_blk_ptr, uint32_t* rb4_ent, void* workspace, int64_t workspace_bytes,
                        gcs_stream stream);
-int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb8_blk_ptr,
-                 const uint32_t* rb8_ent, int64_t n_rows, const float* X, int64_t ldx,
+int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb4_blk_ptr,
+                 const uint32_t* rb4_ent, int64_t n_rows, const float* X, int64_t ldx,
                  const float* scale, const float* shift, const float* alpha, float* Y, int64_t ldy,
                  int32_t H, gcs_stream stream);
 
@@ -218,10 +218,10 @@ typedef struct gcs_batch {
   int64_t ldx;
   const float* y;           /* [B, C] one-hot; NULL for inference */
   const int64_t* seg_ids;       /* [N] graph id of every node (Spektral's i); needed by the pooled backward */
-  const int32_t* rb8_blk_ptr;   /* RB8 form of pattern(A) (gcs_spmm_build_rb8), or NULL */
-  const uint32_t* rb8_ent;
-  const int32_t* rb8_blk_ptr_t; /* RB8 form of pattern(A)^T; may alias when symmetric; backward only */
-  const uint32_t* rb8_ent_t;
+  const int32_t* rb4_blk_ptr;   /* RB4 form of pattern(A) (gcs_spmm_build_rb4), or NULL */
+  const uint32_t* rb4_ent;
+  const int32_t* rb4_blk_ptr_t; /* RB4 form of pattern(A)^T; may alias when symmetric; backward only */
+  const uint32_t* rb4_ent_t;
 } gcs_batch;
 
 /* Number of floats in the flat trainable / state buffers (layout: gcn-string_b200/params.py). */

@@ -31,12 +31,12 @@ def make_batch(n_graphs, n_mean, deg, seed=0):
 
 def run(a, H, mode, iters, transform=True, flush=None):
     lib = _lib.load()
-    lib.gcs_debug_set_spmm_mode({"rows": 1, "rb8": 2}[mode])
+    lib.gcs_debug_set_spmm_mode({"rows": 1, "rb4": 2}[mode])
     n = a.n_rows
     x = torch.randn(n, H, device="cuda")
     y = torch.empty(n, H, device="cuda")
     sc, sh, al = (torch.rand(H, device="cuda") + 0.5, torch.randn(H, device="cuda"), torch.rand(H, device="cuda") * 0.3)
-    kw = dict(rb8=a.rb8) if mode == "rb8" else {}
+    kw = dict(rb4=a.rb4) if mode == "rb4" else {}
     args = (sc, sh, al) if transform else (None, None, None)
     for _ in range(3):
         ops.spmm_sum(a.rowptr, a.colidx, x, *args, out=y, **kw)
@@ -55,7 +55,7 @@ def run(a, H, mode, iters, transform=True, flush=None):
     t = float(np.median(times)) / 1e3
     alg = 4.0 * n * H * 2 + 4.0 * a.nnz + 4.0 * (n + 1)
     return {"H": H, "n_rows": n, "nnz": a.nnz, "deg": a.nnz / n, "mode": mode, "us": t * 1e6,
-            "rb8_ratio": (a.nnz / int(a.rb8[0][-1].item())) if mode == "rb8" else None, "alg_GBs": alg / t / 1e9, "frac_measured_hbm": alg / t / 1e9 / peak(), "edges_per_s": a.nnz / t}
+            "rb4_ratio": (a.nnz / int(a.rb4[0][-1].item())) if mode == "rb4" else None, "alg_GBs": alg / t / 1e9, "frac_measured_hbm": alg / t / 1e9 / peak(), "edges_per_s": a.nnz / t}
 
 
 if __name__ == "__main__":
@@ -77,11 +77,11 @@ if __name__ == "__main__":
         for deg in (4, 8, 16, 32, 64):
             a = make_batch(args.graphs, args.n_mean, deg)
             for H in (16, 32, 64, 128, 256, 512):
-                for mode in ("rows", "rb8"):
-                    if mode == "rb8" and 256 % (H // 4):
+                for mode in ("rows", "rb4"):
+                    if mode == "rb4" and 256 % (H // 4):
                         continue
                     print(json.dumps(run(a, H, mode, args.iters, flush=flush)), flush=True)
     else:
         a = make_batch(args.graphs, args.n_mean, args.deg)
-        for mode in ([args.mode] if args.mode != "auto" else ["rows", "rb8"]):
+        for mode in ([args.mode] if args.mode != "auto" else ["rows", "rb4"]):
             print(json.dumps(run(a, args.hidden, mode, args.iters, transform=not args.no_transform, flush=flush)), flush=True)

@@ -222,9 +222,9 @@ def test_spmm_row_kernel(H, transform):
 
 
 @pytest.mark.parametrize("n_mean,H", [(60, 32), (300, 64), (700, 256), (1400, 32), (90, 1024)])
-def test_spmm_rb8_kernel_matches_row_kernel_bitwise(n_mean, H):
+def test_spmm_rb4_kernel_matches_row_kernel_bitwise(n_mean, H):
     """Both kernels add neighbours in ascending column order with one owner per element, so
-    they must agree bit for bit; the RB8 one is also checked against the oracle."""
+    they must agree bit for bit; the RB4 one is also checked against the oracle."""
     lib = _lib.load()
     ds = synthetic.make_dataset(5, seed=n_mean, n_mean=n_mean, deg=10, n_feat=4)
     ids = np.arange(5, dtype=np.int64)
@@ -237,38 +237,38 @@ def test_spmm_rb8_kernel_matches_row_kernel_bitwise(n_mean, H):
     wide = torch.zeros(n, 3 * H, device="cuda")           # write into a slice: ldy != H
     try:
         lib.gcs_debug_set_spmm_mode(1)
-        y_rows = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al), rb8=a.rb8)   # mode 1 ignores rb8
+        y_rows = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al), rb4=a.rb4)   # mode 1 ignores rb4
     finally:
         lib.gcs_debug_set_spmm_mode(0)
-    y_rb8 = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al), out=wide[:, H:2 * H], rb8=a.rb8).clone()
-    assert np.array_equal(host(y_rb8), host(y_rows))
+    y_rb4 = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al), out=wide[:, H:2 * H], rb4=a.rb4).clone()
+    assert np.array_equal(host(y_rb4), host(y_rows))
     try:
-        lib.gcs_debug_set_spmm_mode(2)                    # RB8 also without the prologue
-        y_id = ops.spmm_sum(a.rowptr, a.colidx, dev(x), rb8=a.rb8)
+        lib.gcs_debug_set_spmm_mode(2)                    # RB4 also without the prologue
+        y_id = ops.spmm_sum(a.rowptr, a.colidx, dev(x), rb4=a.rb4)
     finally:
         lib.gcs_debug_set_spmm_mode(0)
-    # the RB8 structure itself: per block of 8 rows the sorted union of columns with row masks
-    blk_ptr, ent = (host(t) for t in a.rb8)
+    # the RB4 structure itself: per block of 4 rows the sorted union of columns with row masks
+    blk_ptr, ent = (host(t) for t in a.rb4)
     ent = ent.view(np.uint32)
     rp, ci = host(a.rowptr), host(a.colidx)
-    assert blk_ptr[0] == 0 and blk_ptr.shape[0] == (n + 7) // 8 + 1 and blk_ptr[-1] <= a.nnz
-    for b in (0, 3, (n - 1) // 8):
-        rows = range(8 * b, min(8 * b + 8, n))
+    assert blk_ptr[0] == 0 and blk_ptr.shape[0] == (n + 3) // 4 + 1 and blk_ptr[-1] <= a.nnz
+    for b in (0, 3, (n - 1) // 4):
+        rows = range(4 * b, min(4 * b + 4, n))
         want = {}
         for k, r in enumerate(rows):
             for c in ci[rp[r]:rp[r + 1]]:
                 want[int(c)] = want.get(int(c), 0) | (1 << k)
         got = ent[blk_ptr[b]:blk_ptr[b + 1]]
         assert [int(e >> 8) for e in got] == sorted(want) and [int(e & 255) for e in got] == [want[c] for c in sorted(want)]
-    assert blk_ptr[-1] < 0.6 * a.nnz                      # banded graphs: well under one entry per edge
+    assert blk_ptr[-1] < 0.7 * a.nnz                      # banded graphs: well under one entry per edge
     z = x.astype(np.float64) * sc + sh
     csr = sp.csr_matrix((np.ones(a.nnz), ci, rp), shape=(n, n))
-    assert rel_err(host(y_rb8), csr @ np.where(z > 0, z, al * z)) < TOL
+    assert rel_err(host(y_rb4), csr @ np.where(z > 0, z, al * z)) < TOL
     assert rel_err(host(y_id), csr @ x.astype(np.float64)) < TOL
     assert float(wide[:, :H].abs().max()) == 0.0 and float(wide[:, 2 * H:].abs().max()) == 0.0
 
 
-def test_spmm_rb8_arbitrary_structure():
+def test_spmm_rb4_arbitrary_structure():
     """A non-banded random matrix with a few dense rows, empty rows and a ragged last block."""
     lib = _lib.load()
     rng = np.random.default_rng(7)
@@ -281,7 +281,7 @@ def test_spmm_rb8_arbitrary_structure():
     a.sort_indices()
     x = dev(rng.standard_normal((n, 64)).astype(np.float32))
     rp, ci = dev(a.indptr.astype(np.int32)), dev(a.indices.astype(np.int32))
-    rb8 = ops.build_rb8(rp, ci)
+    rb4 = ops.build_rb4(rp, ci)
     try:
         lib.gcs_debug_set_spmm_mode(1)
         y_rows = ops.spmm_sum(rp, ci, x)
@@ -289,7 +289,7 @@ def test_spmm_rb8_arbitrary_structure():
         lib.gcs_debug_set_spmm_mode(0)
     try:
         lib.gcs_debug_set_spmm_mode(2)
-        assert torch.equal(ops.spmm_sum(rp, ci, x, rb8=rb8), y_rows)
+        assert torch.equal(ops.spmm_sum(rp, ci, x, rb4=rb4), y_rows)
     finally:
         lib.gcs_debug_set_spmm_mode(0)
     assert rel_err(host(y_rows), _spmm_ref(a, host(x))) < TOL
