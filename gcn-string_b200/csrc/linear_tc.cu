@@ -1,32 +1,25 @@
 // K1 / K9 on the 5th-generation tensor cores: fp32-accurate dense transforms for widths that
-// are multiples of 256, as 3xTF32 error-compensated products issued with tcgen05.mma.
+// are multiples of 128, as 3xTF32 error-compensated products issued with tcgen05.mma.
 //
 //   C[M, N] (+)= A[M, K] . B[K, N] (+ bias)        A: activations (fp32, any leading dim)
 //                                                   B: weights, pre-split once per call
 // fp32 parity (BASELINE.json: 1e-5 relative) rules out a single TF32/BF16 pass (~1e-3).  Each
-// operand is split a = a_hi + a_lo with a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi), and
+// operand is split a = a_hi + a_lo with a_hi = tf32(a) rounded to nearest, a_lo = a - a_hi, and
 //   A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi      (the dropped A_lo.B_lo term is ~2^-22)
-// accumulates in fp32 in tensor memory: three kind::tf32 MMAs per K step.
+// accumulates in fp32 in tensor memory: three kind::tf32 products per K step.
 //
-// The tensor core adds each K=8 step into the fp32 accumulator with truncation, a bias that grows
-// with the number of steps on a LARGE accumulator (measured 6.6e-6 at K=1024 with one chain).
-// So the main term A_hi.B_hi and the two 2^-11-smaller correction terms accumulate in SEPARATE
-// tensor-memory accumulators and meet in a single fp32 add in the epilogue.
+// The tensor core adds each K=8 step into the fp32 accumulator with TRUNCATION, a bias that grows
+// with the number of steps of a chain (~n * 2^-26).  So the main term A_hi.B_hi and the 2^-11-smaller
+// correction terms accumulate in SEPARATE tensor-memory accumulators that meet in fp32 adds in the
+// epilogue, and chains are kept short: forward / dX reductions longer than 512 are chunked (launch()),
+// the weight gradient folds its chains into a running fp32 sum every 16 K blocks.
 //
-// One CTA = one 128 x 128 output tile, 192 threads, warp-specialised:
-//   warp 0      TMA producer: raw fp32 A tile [128 x 32] and the two pre-split weight tiles
-//               [128 x 32] (K-major, 128 B rows, SWIZZLE_128B) per stage, 4 stages
-//   warp 1      MMA issuer (one elected thread): per stage 4 K-steps x 3 tcgen05.mma with the
-//               A operand in TENSOR MEMORY and B from shared memory; owns TMEM alloc/free
-//   warps 2-9   converters: each thread owns half a row of the A tile, reads its 64 B from the
-//               swizzled shared tile (conflict-free), splits hi/lo in registers and writes
-//               both halves into TMEM (tcgen05.st) - the split never touches shared memory,
-//               which the B operand already keeps busy; afterwards the same warps run the
-//               epilogue (tcgen05.ld -> + bias / + C -> 128 B-per-thread row stores)
-// TMEM: columns [0, 128) main accumulator, [128, 256) correction accumulator, [256, 512) four A
-// stages of (32 hi + 32 lo) columns (ncu: with 4 converter warps and 2 stages the tensor pipe was
-// only 58% busy, waiting for the split operand).  The two CTAs that share a row block (N = 256) are adjacent
-// in launch order, so the second read of the A tile is an L2 hit.
+// Two kernels (profiles/r01_gemm_kernels.md has the measurement behind every structural choice):
+//   linear_tc_pair_kernel   forward and input gradient: persistent CTA pairs (cta_group::2), A operand
+//                           split by converter warps straight into TENSOR MEMORY (TS-mode MMA), weight
+//                           tiles split across the pair, TMA-store / reduce-add epilogue
+//   wgrad_tc_kernel         weight gradient: reduction over the rows, A^T gathered into tensor memory,
+//                           dH split in shared memory as an MN-major operand
 #include <cuda.h>
 
 #include "common.cuh"
@@ -36,14 +29,10 @@ namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int kStages = 4;    // shared-memory stages (TMA)
-constexpr int kAStages = 4;   // tensor-memory stages of the split A operand (forward / dX kernel)
 constexpr int kWgAStages = 2; // ... of the weight-gradient kernel (it also keeps a running sum in TMEM)
 constexpr int kConvWarps = 8; // converter warps: two per TMEM lane quarter, 16 of the 32 K columns each
 constexpr int kThreads = 64 + 32 * kConvWarps;
 constexpr uint32_t A_RAW_BYTES = BM * BK * 4;          // 16 KB
-constexpr uint32_t B_BYTES = BN * BK * 4;              // 16 KB per half
-constexpr uint32_t STAGE_BYTES = A_RAW_BYTES + 2 * B_BYTES;
-constexpr uint32_t kSmemBytes = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t ACC_MAIN = 0, ACC_CORR = 128, A_COL = 256, kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -143,188 +132,10 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor: D = F32, A = B = TF32, both K-major, M = BM, N = BN or 2*BN.
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
-                                (static_cast<uint32_t>(BM >> 4) << 24);
-constexpr uint32_t kInstrDesc2N = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>((2 * BN) >> 3) << 17) |
-                                  (static_cast<uint32_t>(BM >> 4) << 24);
-
-__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(
-    const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
-    const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C, int64_t ldc,
-    const float* __restrict__ bias, int64_t M, int K, int accumulate, const float* __restrict__ rowbias,
-    int64_t ld_rowbias, const int64_t* __restrict__ seg) {
-  extern __shared__ uint8_t smem_dyn[];
-  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024 B alignment
-  const uint32_t bars = base + kStages * STAGE_BYTES;
-  // barriers (8 B each): full[4] | smem_empty[4] | a_ready[4] | a_empty[4] | acc_full | tmem ptr
-  auto full = [&](int s) { return bars + 8u * s; };
-  auto smem_empty = [&](int s) { return bars + 32u + 8u * s; };
-  auto a_ready = [&](int t) { return bars + 64u + 8u * t; };
-  auto a_empty = [&](int t) { return bars + 96u + 8u * t; };
-  const uint32_t acc_full = bars + 128u;
-  const uint32_t tmem_slot = bars + 136u;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;     // the N tiles of one row block are adjacent in launch order
-  const int m0 = blockIdx.y * BM;
-  // Measured on B200 and NOT kept: a 2-CTA cluster with TMA multicast of the weight tiles (same
-  // time: the bound is the ~40 B/clk each SM can ingest, and a multicast byte is still ingested),
-  // 8 vs 4 converter warps, 4 vs 2 tensor-memory stages, 8 vs 12 MMA issues per K block (all within
-  // 2%).  The mainloop runs at ~1220 clk per K block = 48 KB / 39 B/clk; see DESIGN.md 3.2.
-  const int num_kb = K / BK;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full(s), 1);
-      mbar_init(smem_empty(s), 1 + kConvWarps);   // one tcgen05.commit + one arrive per converter warp
-    }
-    for (int t = 0; t < kAStages; ++t) {
-      mbar_init(a_ready(t), 32 * kConvWarps);
-      mbar_init(a_empty(t), 1);
-    }
-    mbar_init(acc_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(smem_empty(s), ((kb / kStages) & 1) ^ 1);
-        const uint32_t a_raw = base + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(full(s), STAGE_BYTES);
-        tma_load_2d(a_raw, &map_a, kb * BK, m0, full(s));
-        tma_load_2d(a_raw + A_RAW_BYTES, &map_b_hi, kb * BK, n0, full(s));
-        tma_load_2d(a_raw + A_RAW_BYTES + B_BYTES, &map_b_lo, kb * BK, n0, full(s));
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
-    {
-      const uint32_t leader = elect_one();
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages, t = kb % kAStages;
-        mbar_wait(full(s), (kb / kStages) & 1);        // weight tiles landed
-        mbar_wait(a_ready(t), (kb / kAStages) & 1);    // converters filled this TMEM A stage
-        tc_fence_after();
-        if (leader) {
-          const uint32_t b_hi = base + s * STAGE_BYTES + A_RAW_BYTES;
-          const uint64_t d_hi = make_kmajor_sw128_desc(b_hi);
-          const uint32_t a_hi = tmem_base + A_COL + t * 64;
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // K advance inside the 128 B swizzle atom: +32 B on the start address, +8 TMEM columns
-            const uint64_t koff = static_cast<uint64_t>((k * 32) >> 4);
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            // A_hi meets BOTH weight halves in one N = 256 instruction: the hi and lo weight tiles are adjacent in
-            // shared memory (one 256-row K-major operand) and the main and correction accumulators are adjacent in
-            // tensor memory.
-            mma_tf32_ts(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kInstrDesc2N, acc);      // A_hi . [B_hi | B_lo]
-            mma_tf32_ts(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kInstrDesc, 1u);    // A_lo . B_hi
-          }
-          tc_commit(smem_empty(s));           // weight tiles of this stage consumed
-          tc_commit(a_empty(t));              // TMEM A stage consumed
-        }
-        __syncwarp();
-      }
-      if (leader) tc_commit(acc_full);
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------------------ converters, then epilogue
-    const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                  // which 16 of the 32 K columns (and, later, output columns)
-    const int r = quarter * 32 + lane;                 // row of the tile owned by this thread
-    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % kStages, t = kb % kAStages;
-      mbar_wait(full(s), (kb / kStages) & 1);
-      const uint32_t row_addr = base + s * STAGE_BYTES + r * 128;
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float4 v;
-        const uint32_t addr = row_addr + (((4 * half + c) ^ (r & 7)) << 4);          // undo the 128 B TMA swizzle
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-        const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(e[i], hi[4 * c + i], lo[4 * c + i]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_empty(s));       // raw A tile consumed by this warp
-      mbar_wait(a_empty(t), ((kb / kAStages) & 1) ^ 1);   // MMAs of the previous use of this TMEM stage are done
-      tc_fence_after();
-      const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64 + 16 * half;
-      tmem_st16(a_hi, hi);
-      tmem_st16(a_hi + 32, lo);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      mbar_arrive(a_ready(t));
-    }
-    // epilogue: 4 chunks of 32 columns per thread-row, main + correction accumulators
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int64_t row = static_cast<int64_t>(m0) + r;
-    // optional per-row bias gathered through a segment index: C[row] += rowbias[seg[row]] (the
-    // gradient of the global sum pool, broadcast to the nodes of each graph, fused here)
-    const float* rb = (rowbias && row < M) ? rowbias + __ldg(seg + row) * ld_rowbias + n0 : nullptr;
-#pragma unroll 1
-    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-      uint32_t v[32], w[32];
-      tmem_ld32(tmem_base + lane_addr + ACC_MAIN + c0, v);
-      tmem_ld32(tmem_base + lane_addr + ACC_CORR + c0, w);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
-        float* cp = C + row * ldc + n0 + c0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(w[4 * q]),
-                                 __uint_as_float(v[4 * q + 1]) + __uint_as_float(w[4 * q + 1]),
-                                 __uint_as_float(v[4 * q + 2]) + __uint_as_float(w[4 * q + 2]),
-                                 __uint_as_float(v[4 * q + 3]) + __uint_as_float(w[4 * q + 3]));
-          if (bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (rb) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + q);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (accumulate) {
-            const float4 old = *reinterpret_cast<const float4*>(cp + 4 * q);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          *reinterpret_cast<float4*>(cp + 4 * q) = o;
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// CTA-PAIR variant of the forward / dX kernel (tcgen05 cta_group::2).
+// Forward / dX kernel: persistent CTA pairs (tcgen05 cta_group::2).
 //
-// ncu on the single-CTA kernel above (profiles/r01_gemm_fwd_k1024.md): 12.7 GB of TMA loads per
+// ncu on the one-CTA-per-tile kernel this replaced (profiles/r01_gemm_kernels.md): 12.7 GB of TMA loads per
 // launch at 9.3 TB/s = the ~42 B/clk/SM the L2 -> SM fabric delivers; the tensor pipe waits for
 // the weight tiles, which every CTA streams in full (32 KB of the 48 KB per K block).  A CTA pair
 // computes a 256 x 128 tile with ONE copy of the weight tiles split across the two SMs: each CTA
@@ -889,7 +700,7 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t in
 
 bool shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* C, int64_t ldc, const float* bias) {
   return M > 0 && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(C) &&
-         (!bias || aligned16(bias)) && ceil_div(M, BM) < 65535;
+         (!bias || aligned16(bias)) && ceil_div(M, 2 * BM) * (N / BN) < (1LL << 30);
 }
 
 int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, float* hi, float* lo,
@@ -899,55 +710,39 @@ int64_t split_workspace_bytes(int K, int N) { return round_up(2LL * K * N * size
 
 static int g_max_chain_k = 512;                          // longest tensor-core accumulation chain of the forward / dX kernel
 void set_max_chain_k(int k) { if (k >= BK && k % BK == 0) g_max_chain_k = k; }
-static int g_pair_mode = 1;                               // 1 = CTA-pair kernel (default), 0 = single-CTA kernel
-void set_pair_mode(int m) { g_pair_mode = m; }
 
 // Bt: weights already split, laid out [N][K] (reduction contiguous): hi at Bt, lo at Bt + N*K.
 int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, const float* bias, float* C, int64_t ldc,
            int64_t M, int K, int N, int accumulate, cudaStream_t st, const float* rowbias, int64_t ld_rowbias,
            const int64_t* seg) {
   alignas(64) CUtensorMap ma, mh, ml, mc;
-  if (g_pair_mode && ceil_div(M, 2 * BM) * (N / BN) < (1LL << 30)) {
-    GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));        // output boxes of 32 rows x 32 columns (128 B rows, SWIZZLE_128B)
-    static bool attr2 = false;
-    if (!attr2) {
-      GCS_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
-      attr2 = true;
-    }
-    const int n_tiles = N / BN;
-    const int num_tiles = static_cast<int>(ceil_div(M, 2 * BM)) * n_tiles;
-    const int pairs = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;      // persistent: one CTA pair per SM pair
-    dim3 grid(2, pairs);                                                           // x = rank in the pair
-    // The tensor core adds every K = 8 step into the fp32 accumulator with TRUNCATION: a chain of n steps shrinks the
-    // result by ~n * 2^-26 (measured 2e-5 on the BatchNorm variances of a hidden-512 model with K = 2048 in one chain;
-    // with chains of 1024 one gradient tensor of that model was 1.4e-5 off the float64 oracle, with 512 all are inside
-    // max(1e-5, 4 x the error of a float32 CPU run)).  Longer reductions therefore run as chunks of <= 512 (64 steps)
-    // that meet in C through the epilogue's round-to-nearest reduce-add: +3% on the hidden-512 step.
-    const int kMaxChainK = g_max_chain_k;
-    for (int k0 = 0; k0 < K; k0 += kMaxChainK) {
-      const int kc = K - k0 < kMaxChainK ? K - k0 : kMaxChainK;
-      GCS_TRY(make_map(&ma, A + k0, M, kc, lda, BM));
-      GCS_TRY(make_map(&mh, Bt_hi + k0, N, kc, K, 64));
-      GCS_TRY(make_map(&ml, Bt_lo + k0, N, kc, K, 64));
-      const bool first = k0 == 0;
-      linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
-                                                                 first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
-                                                                 seg);
-      GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
-    }
-    return GCS_OK;
-  }
-  GCS_TRY(make_map(&ma, A, M, K, lda, BM));
-  GCS_TRY(make_map(&mh, Bt_hi, N, K, K, BN));
-  GCS_TRY(make_map(&ml, Bt_lo, N, K, K, BN));
+  GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));        // output boxes of 32 rows x 32 columns (128 B rows, SWIZZLE_128B)
   static bool attr = false;
   if (!attr) {
-    GCS_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    GCS_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     attr = true;
   }
-  dim3 grid(N / BN, static_cast<unsigned>(ceil_div(M, BM)));
-  linear_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ma, mh, ml, C, ldc, bias, M, K, accumulate, rowbias, ld_rowbias, seg);
-  GCS_CHECK_LAUNCH("linear_tc_kernel");
+  const int n_tiles = N / BN;
+  const int num_tiles = static_cast<int>(ceil_div(M, 2 * BM)) * n_tiles;
+  const int pairs = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;      // persistent: one CTA pair per SM pair
+  dim3 grid(2, pairs);                                                           // x = rank in the pair
+  // The tensor core adds every K = 8 step into the fp32 accumulator with TRUNCATION: a chain of n steps shrinks the
+  // result by ~n * 2^-26 (measured 2e-5 on the BatchNorm variances of a hidden-512 model with K = 2048 in one chain;
+  // with chains of 1024 one gradient tensor of that model was 1.4e-5 off the float64 oracle, with 512 all are inside
+  // max(1e-5, 4 x the error of a float32 CPU run)).  Longer reductions therefore run as chunks of <= 512 (64 steps)
+  // that meet in C through the epilogue's round-to-nearest reduce-add: +3% on the hidden-512 step.
+  const int kMaxChainK = g_max_chain_k;
+  for (int k0 = 0; k0 < K; k0 += kMaxChainK) {
+    const int kc = K - k0 < kMaxChainK ? K - k0 : kMaxChainK;
+    GCS_TRY(make_map(&ma, A + k0, M, kc, lda, BM));
+    GCS_TRY(make_map(&mh, Bt_hi + k0, N, kc, K, 64));
+    GCS_TRY(make_map(&ml, Bt_lo + k0, N, kc, K, 64));
+    const bool first = k0 == 0;
+    linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
+                                                               first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
+                                                               seg);
+    GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
+  }
   return GCS_OK;
 }
 

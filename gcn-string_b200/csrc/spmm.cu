@@ -246,12 +246,11 @@ int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 whenever supplie
 
 // Test / sweep hook (not part of the drop-in surface).
 extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
-namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_pair_mode(int m); void set_max_chain_k(int k); } }
+namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
   if (id == 2 && value > 0) g_rb4_iters = value;
   if (id == 3) gcs::tc::set_wgrad_chain(value);
-  if (id == 4) gcs::tc::set_pair_mode(value);
   if (id == 5) gcs::tc::set_max_chain_k(value);
 }
 

@@ -5,7 +5,6 @@ import numpy as np, torch
 import gcn_string_b200 as g
 from gcn_string_b200 import _lib, synthetic
 lib = _lib.load()
-if len(sys.argv) > 1: lib.gcs_debug_set_param(4, int(sys.argv[1]))
 ds = synthetic.make_dataset(1024, seed=0, n_mean=500, deg=12, n_feat=32)
 loader = g.DisjointLoader(ds, batch_size=1024, epochs=None, shuffle=False, symmetric=True, device_resident=True)
 model = g.GeneralGNN(2, activation="softmax", hidden=256, message_passing=4, seed=0); model.build(32)

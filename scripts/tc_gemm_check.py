@@ -74,8 +74,6 @@ def bench(M, K, N, iters=10):
     return r
 
 if __name__ == "__main__":
-    if "--single" in sys.argv:
-        lib.gcs_debug_set_param(4, 0)        # single-CTA kernel instead of the CTA-pair kernel
     for shape in [(128, 32, 256), (300, 64, 256), (1000, 256, 256), (4096, 1024, 256), (777, 1280, 512), (70001, 256, 256)]:
         print(json.dumps(check(*shape)), flush=True)
     if "--bench" in sys.argv:
