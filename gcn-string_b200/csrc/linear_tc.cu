@@ -662,6 +662,215 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair form of the weight gradient (K_in % 256 == 0).  The one-CTA kernel above is bound by shared-memory
+// bandwidth: per K block it moves TMA 32 KB + A^T gather 16 KB + dH split 16 KB read / 32 KB written + MMA operand
+// reads 48 KB = 144 KB at 128 B/clk = 1125 clk against 768 clk of tensor work (profiles/r01_gemm_kernels.md).  A pair
+// computes a 256 x 128 tile of dW: each CTA converts its own 128 columns of the A slab but lands, splits and feeds
+// only HALF of the dH slab (64 columns), 88 KB per K block and SM.  Accumulators stay [main | correction] of 128
+// columns each (three N = 128 instructions per K step) so that the running sum of the chain folds still fits TMEM.
+// Protocol as in linear_tc_pair_kernel: the leader CTA issues, converters / splitters / accumulator warps of both
+// CTAs arrive on the leader's barriers (one remote arrive per warp), tcgen05.commit multicasts the releases.
+constexpr int kWgPStages = 6;
+constexpr uint32_t WGP_Y_BYTES = 32 * 64 * 4;            // 8 KB: this CTA's half of the dH slab (two 32-column boxes)
+constexpr uint32_t WGP_STAGE_BYTES = WG_X_BYTES + 2 * WGP_Y_BYTES;   // 32 KB
+constexpr uint32_t kWgPSmemBytes = kWgPStages * WGP_STAGE_BYTES + 1024 + 256;
+// D = F32, A = B = TF32, A K-major (TMEM), B MN-major, N = 128, M = 256 across the pair
+constexpr uint32_t kWgPairDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | (static_cast<uint32_t>(128 >> 3) << 17) |
+                                 (static_cast<uint32_t>(256 >> 4) << 24);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad_tc_pair_kernel(
+    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+    float* __restrict__ out, int64_t out_split_stride, int ldo, int num_kb_total, int kb_per_split, int kWgChain,
+    int k_rows) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bars = base + kWgPStages * WGP_STAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto smem_empty = [&](int s) { return bars + 48u + 8u * s; };
+  auto y_ready = [&](int s) { return bars + 96u + 8u * s; };
+  auto a_ready = [&](int t) { return bars + 144u + 8u * t; };
+  auto a_empty = [&](int t) { return bars + 160u + 8u * t; };
+  const uint32_t acc_full = bars + 176u, acc_empty = bars + 184u, tmem_slot = bars + 192u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = blockIdx.x & 1;
+  const int i0 = (blockIdx.x >> 1) * 256 + rank * 128;   // this CTA's rows of dW = its columns of the A slab
+  const int j0 = blockIdx.y * 128;
+  const int jh = j0 + 64 * rank;                         // this CTA's half of the dH columns
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;                 // host guarantees >= 1
+  out += static_cast<int64_t>(blockIdx.z) * out_split_stride;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y));
+    for (int s = 0; s < kWgPStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(smem_empty(s), 1);
+      mbar_init(y_ready(s), 8);                   // one arrive per splitter warp of both CTAs (leader's copy is used)
+    }
+    for (int t = 0; t < kWgAStages; ++t) {
+      mbar_init(a_ready(t), 8);                   // one arrive per A^T converter warp of both CTAs
+      mbar_init(a_empty(t), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);                      // one arrive per accumulator warp of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kWgPStages;
+        mbar_wait(smem_empty(s), ((kb / kWgPStages) & 1) ^ 1);
+        const uint32_t xs = base + s * WGP_STAGE_BYTES;
+        const int m = (kb_begin + kb) * 32;
+        mbar_arrive_expect_tx(full(s), WG_X_BYTES + WGP_Y_BYTES);
+        tma_load_2d(xs, &map_x, i0, m, full(s));
+        tma_load_2d(xs + WG_X_BYTES, &map_y, jh, m, full(s));
+        tma_load_2d(xs + WG_X_BYTES + 4096, &map_y, jh + 32, m, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t leader = elect_one();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kWgPStages, t = kb % kWgAStages;
+        const int chain = kb / kWgChain, pos = kb % kWgChain;
+        if (pos == 0 && chain > 0) mbar_wait(acc_empty, (chain - 1) & 1);   // accumulators of both CTAs drained
+        mbar_wait(a_ready(t), (kb / kWgAStages) & 1);     // A^T of both CTAs is in tensor memory
+        mbar_wait(y_ready(s), (kb / kWgPStages) & 1);     // both halves of the dH slab are split
+        tc_fence_after();
+        if (leader) {
+          const uint32_t y_hi = base + s * WGP_STAGE_BYTES + WG_X_BYTES;
+          const uint64_t d_hi = make_mnmajor_b32_desc(y_hi);
+          const uint64_t d_lo = make_mnmajor_b32_desc(y_hi + WGP_Y_BYTES);
+          const uint32_t a_hi = tmem_base + A_COL + t * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * 8 * 128) >> 4);       // 8 rows of 128 B per K step
+            const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
+            mma_tf32_ts_pair(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kWgPairDesc, acc);
+            mma_tf32_ts_pair(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kWgPairDesc, acc);
+            mma_tf32_ts_pair(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kWgPairDesc, 1u);
+          }
+          tc_commit_pair(smem_empty(s));
+          tc_commit_pair(a_empty(t));
+          if (pos == kWgChain - 1 || kb == num_kb - 1) tc_commit_pair(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ A^T converters: column i of the A slab -> TMEM
+    const int quarter = warp & 3;
+    const int i = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kWgPStages, t = kb % kWgAStages;
+      mbar_wait(full(s), (kb / kWgPStages) & 1);
+      const uint32_t xs = base + s * WGP_STAGE_BYTES;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int m = 0; m < 32; ++m) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (m * 128 + i) * 4));
+        split_tf32(v, hi[m], lo[m]);
+      }
+      mbar_wait(a_empty(t), ((kb / kWgAStages) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64;
+      tmem_st32(a_hi, hi);
+      tmem_st32(a_hi + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(a_ready(t));
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ dH splitters: this CTA's 64 columns, hi in place,
+    // lo into the two boxes right behind
+    const int ct = (warp - 6) * 32 + lane;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kWgPStages;
+      mbar_wait(full(s), (kb / kWgPStages) & 1);
+      const uint32_t ys = base + s * WGP_STAGE_BYTES + WG_X_BYTES;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t addr = ys + (ct + 128 * u) * 16;
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+        uint32_t h4[4], l4[4];
+        split_tf32(v.x, h4[0], l4[0]); split_tf32(v.y, h4[1], l4[1]);
+        split_tf32(v.z, h4[2], l4[2]); split_tf32(v.w, h4[3], l4[3]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h4[0]), "r"(h4[1]), "r"(h4[2]), "r"(h4[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + WGP_Y_BYTES), "r"(l4[0]), "r"(l4[1]), "r"(l4[2]), "r"(l4[3]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the tensor cores
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(y_ready(s));
+    }
+  } else {
+    // ------------------------------------------------------------ accumulators (each CTA folds its own 128 rows)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int num_chains = (num_kb + kWgChain - 1) / kWgChain;
+    for (int chain = 0; chain < num_chains; ++chain) {
+      mbar_wait(acc_full, chain & 1);
+      tc_fence_after();
+      const bool last = chain == num_chains - 1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32], w[32], run[32];
+        tmem_ld32(tmem_base + lane_addr + ACC_MAIN + c0, v);
+        tmem_ld32(tmem_base + lane_addr + ACC_CORR + c0, w);
+        if (chain > 0) tmem_ld32(tmem_base + lane_addr + RUN_COL + c0, run);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          float x = __uint_as_float(v[q]) + __uint_as_float(w[q]);
+          if (chain > 0) x += __uint_as_float(run[q]);
+          run[q] = __float_as_uint(x);
+        }
+        if (!last) {
+          tmem_st32(tmem_base + lane_addr + RUN_COL + c0, run);
+        } else if (i0 + r < k_rows) {
+          float* op = out + static_cast<int64_t>(i0 + r) * ldo + j0 + c0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(op + 4 * q) = make_float4(__uint_as_float(run[4 * q]), __uint_as_float(run[4 * q + 1]),
+                                                                 __uint_as_float(run[4 * q + 2]), __uint_as_float(run[4 * q + 3]));
+        }
+      }
+      if (!last) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(acc_empty);
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -753,13 +962,23 @@ bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const 
          M < (1LL << 31) - 64;
 }
 
+static int g_wg_pair = 1;                                // debug knob: 0 = always the one-CTA kernel
+void set_wgrad_pair(int v) { g_wg_pair = v; }
+static bool wgrad_use_pair(int K) { return g_wg_pair && K % 256 == 0; }
+
 // Number of row splits (grid.z) and K blocks per split for the weight-gradient kernel.
 void wgrad_split(int64_t M, int K, int N, int* splits, int* kb_per_split) {
-  const int64_t tiles = ceil_div(K, 128) * (N / 128);
   const int64_t nkb = ceil_div(M, 32);
-  int64_t s = ceil_div(4LL * sm_count(), tiles);
   const int kWgChain = g_wg_chain;
   const int64_t max_s = ceil_div(nkb, kWgChain);          // at least one full chain per split
+  int64_t s;
+  if (wgrad_use_pair(K)) {
+    const int64_t tiles = (K / 256) * (N / 128);          // 256 x 128 tiles, one CTA pair each: ONE wave of pairs
+    s = (sm_count() / 2) / tiles;
+  } else {
+    const int64_t tiles = ceil_div(K, 128) * (N / 128);
+    s = ceil_div(4LL * sm_count(), tiles);
+  }
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   int64_t per = ceil_div(nkb, s);
@@ -780,6 +999,18 @@ int wgrad_launch(const float* A, int64_t lda, const float* dH, int64_t ldh, floa
   alignas(64) CUtensorMap mx, my;
   GCS_TRY(make_map(&mx, A, M, K, lda, 32, 128, CU_TENSOR_MAP_SWIZZLE_NONE));
   GCS_TRY(make_map(&my, dH, M, N, ldh, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  if (wgrad_use_pair(K)) {
+    static bool attr2 = false;
+    if (!attr2) {
+      GCS_CUDA(cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgPSmemBytes));
+      attr2 = true;
+    }
+    dim3 grid(static_cast<unsigned>(2 * (K / 256)), N / 128, splits);       // x = 2 * tile + rank in the pair
+    wgrad_tc_pair_kernel<<<grid, kWgThreads, kWgPSmemBytes, st>>>(mx, my, out, static_cast<int64_t>(K) * N, N,
+                                                                static_cast<int>(ceil_div(M, 32)), kb_per_split, g_wg_chain, K);
+    GCS_CHECK_LAUNCH("wgrad_tc_pair_kernel");
+    return GCS_OK;
+  }
   static bool attr = false;
   if (!attr) {
     GCS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));

@@ -246,12 +246,13 @@ int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 whenever supplie
 
 // Test / sweep hook (not part of the drop-in surface).
 extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
-namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); } }
+namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); void set_wgrad_pair(int v); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
   if (id == 2 && value > 0) g_rb4_iters = value;
   if (id == 3) gcs::tc::set_wgrad_chain(value);
   if (id == 5) gcs::tc::set_max_chain_k(value);
+  if (id == 4) gcs::tc::set_wgrad_pair(value);
 }
 
 extern "C" int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows) {
