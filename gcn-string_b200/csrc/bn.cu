@@ -69,6 +69,15 @@ __device__ __forceinline__ void block_store_partials(double (&v)[NV], double* __
   (void)col_stride; (void)ncols_valid;
 }
 
+// Final combine of per-split partials, one WARP per column: lane l adds splits l, l+32, ... in order, then the 32
+// lane sums meet in a fixed shuffle tree - deterministic, and ~20x shorter than one thread walking all ~300 splits
+// (the three "final" kernels were 40-65 us each, latency-bound: 1.2 ms per train step).
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;                                             // valid in lane 0
+}
+
 // partial layout: ws[(split * C + c) * Q + q], Q quantities per column.
 template <int VEC>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(
@@ -102,20 +111,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_partial_kernel(
   block_store_partials<2 * VEC>(acc, ws + (static_cast<int64_t>(blockIdx.y) * C + c) * 2, 0, 0, c < C);
 }
 
-__global__ void bn_stats_final_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
-                                      float* __restrict__ mean, float* __restrict__ var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_stats_final_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
+                                                             float* __restrict__ mean, float* __restrict__ var) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < splits; ++k) {
+  for (int k = lane; k < splits; k += 32) {
     s += ws[(static_cast<int64_t>(k) * C + c) * 2];
     q += ws[(static_cast<int64_t>(k) * C + c) * 2 + 1];
   }
-  const double m = s / static_cast<double>(M);
-  double v = q / static_cast<double>(M) - m * m;
-  if (v < 0.0) v = 0.0;
-  mean[c] = static_cast<float>(m);
-  var[c] = static_cast<float>(v);
+  s = warp_sum_fixed(s);
+  q = warp_sum_fixed(q);
+  if (lane == 0) {
+    const double m = s / static_cast<double>(M);
+    double v = q / static_cast<double>(M) - m * m;
+    if (v < 0.0) v = 0.0;
+    mean[c] = static_cast<float>(m);
+    var[c] = static_cast<float>(v);
+  }
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var,
@@ -260,17 +273,21 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(
 
 // Per column for the apply pass: coef[4c..4c+3] = {S1/M, S2/M, rstd, gamma*rstd}; dgamma/dbeta/dalpha
 // are written here.
-__global__ void bn_bwd_final_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
-                                    const float* __restrict__ var, const float* __restrict__ gamma, float eps,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    float* __restrict__ dalpha, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_final_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
+                                                           const float* __restrict__ var, const float* __restrict__ gamma,
+                                                           float eps, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ dalpha, float* __restrict__ coef) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for (int k = 0; k < splits; ++k) {
+  for (int k = lane; k < splits; k += 32) {
     const double* p = ws + (static_cast<int64_t>(k) * C + c) * 3;
     s1 += p[0]; s2 += p[1]; s3 += p[2];
   }
+  s1 = warp_sum_fixed(s1);
+  s2 = warp_sum_fixed(s2);
+  s3 = warp_sum_fixed(s3);
+  if (lane != 0) return;
   if (dbeta) dbeta[c] = static_cast<float>(s1);
   if (dgamma) dgamma[c] = static_cast<float>(s2);
   if (dalpha) dalpha[c] = static_cast<float>(s3);
@@ -372,12 +389,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
   if (colsum_ws) block_store_partials<VEC>(csum, colsum_ws + static_cast<int64_t>(blockIdx.y) * C + c, 0, 0, valid);
 }
 
-__global__ void bn_bwd_dbias_final_kernel(const double* __restrict__ ws, int splits, int C, float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_dbias_final_kernel(const double* __restrict__ ws, int splits, int C,
+                                                                 float* __restrict__ dbias) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0;
-  for (int k = 0; k < splits; ++k) s += ws[static_cast<int64_t>(k) * C + c];
-  dbias[c] = static_cast<float>(s);
+  for (int k = lane; k < splits; k += 32) s += ws[static_cast<int64_t>(k) * C + c];
+  s = warp_sum_fixed(s);
+  if (lane == 0) dbias[c] = static_cast<float>(s);
 }
 
 }  // namespace gcs
@@ -411,7 +430,7 @@ extern "C" int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, f
   if (vec) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
   else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
   GCS_CHECK_LAUNCH("bn_stats_partial_kernel");
-  bn_stats_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, M, mean, var);
+  bn_stats_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, mean, var);
   GCS_CHECK_LAUNCH("bn_stats_final_kernel");
   return GCS_OK;
 }
@@ -464,14 +483,14 @@ extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, i
   if (vec) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
   else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
   GCS_CHECK_LAUNCH("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, M, var, gamma, eps, dgamma, dbeta, dalpha, coef);
+  bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, var, gamma, eps, dgamma, dbeta, dalpha, coef);
   GCS_CHECK_LAUNCH("bn_bwd_final_kernel");
   double* cws = dbias ? ws : nullptr;          // the reduction partials are consumed: reuse their space
   if (vec) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);
   else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);
   GCS_CHECK_LAUNCH("bn_bwd_apply_kernel");
   if (dbias) {
-    bn_bwd_dbias_final_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(ws, g.splits, C, dbias);
+    bn_bwd_dbias_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, dbias);
     GCS_CHECK_LAUNCH("bn_bwd_dbias_final_kernel");
   }
   return GCS_OK;
