@@ -193,42 +193,54 @@ __global__ void tr_count_kernel(const int32_t* __restrict__ colidx, int64_t nnz,
   if (e < nnz) atomicAdd(cnt + colidx[e], 1);   // integer atomics: order-independent result
 }
 
-// Exclusive scan of cnt[0..n) into out[0..n], chunked single-CTA (n up to a few million
-// int32: bandwidth-trivial next to the SpMM it serves).
+// Exclusive scan of cnt[0..n) into out[0..n], chunked single-CTA (n up to a few million int32:
+// bandwidth-trivial next to the SpMM it serves).  Per chunk of 16 K elements: 16 per thread, a
+// shuffle scan inside each warp, one shuffle scan of the 32 warp totals - two barriers per chunk
+// (a shared-memory Hillis-Steele scan with 20 barriers per 8 K chunk took 107 us for the 127 K row
+// blocks of a cfg2 batch).
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ cnt, int64_t n,
                                                               int32_t* __restrict__ out) {
-  __shared__ int32_t s[1024];
-  __shared__ int32_t carry;
-  const int t = threadIdx.x;
-  if (t == 0) carry = 0;
-  __syncthreads();
-  constexpr int PER = 8;
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry_s;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  constexpr int PER = 16;
+  int32_t carry = 0;
   for (int64_t base = 0; base < n; base += 1024 * PER) {
     int32_t v[PER];
     int32_t sum = 0;
     const int64_t b = base + static_cast<int64_t>(t) * PER;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-      v[k] = (b + k < n) ? cnt[b + k] : 0;
+      v[k] = (b + k < n) ? __ldg(cnt + b + k) : 0;
       sum += v[k];
     }
-    s[t] = sum;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      int32_t a = (t >= off) ? s[t - off] : 0;
-      __syncthreads();
-      s[t] += a;
-      __syncthreads();
+    int32_t inc = sum;                                   // inclusive scan of the thread sums inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
     }
-    int32_t run = carry + s[t] - sum;
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = warp_tot[lane], winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += y;
+      }
+      warp_tot[lane] = winc - w;                         // exclusive offsets of the warps
+      if (lane == 31) carry_s = winc;                    // chunk total
+    }
+    __syncthreads();
+    int32_t run = carry + warp_tot[warp] + inc - sum;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       if (b + k < n) out[b + k] = run;
       run += v[k];
     }
-    __syncthreads();
-    if (t == 1023) carry += s[t];
-    __syncthreads();
+    carry += carry_s;
+    __syncthreads();                                     // warp_tot / carry_s are rewritten by the next chunk
   }
   if (t == 0) out[n] = carry;
 }
