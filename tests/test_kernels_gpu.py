@@ -266,6 +266,18 @@ def test_spmm_rb4_kernel_matches_row_kernel_bitwise(n_mean, H):
     assert rel_err(host(y_rb4), csr @ np.where(z > 0, z, al * z)) < TOL
     assert rel_err(host(y_id), csr @ x.astype(np.float64)) < TOL
     assert float(wide[:, :H].abs().max()) == 0.0 and float(wide[:, 2 * H:].abs().max()) == 0.0
+    # slopes above 1 and negative slopes
+    al2 = al.copy()
+    al2[::3] = 1.7
+    al2[1::5] = -0.3
+    try:
+        lib.gcs_debug_set_spmm_mode(1)
+        y_rows2 = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al2))
+    finally:
+        lib.gcs_debug_set_spmm_mode(0)
+    y_rb4_2 = ops.spmm_sum(a.rowptr, a.colidx, dev(x), dev(sc), dev(sh), dev(al2), rb4=a.rb4)
+    assert np.array_equal(host(y_rb4_2), host(y_rows2))
+    assert rel_err(host(y_rb4_2), csr @ np.where(z > 0, z, al2 * z)) < TOL
 
 
 def test_spmm_rb4_arbitrary_structure():
