@@ -11,7 +11,7 @@
 // The tensor core adds each K=8 step into the fp32 accumulator with TRUNCATION, a bias that grows
 // with the number of steps of a chain (~n * 2^-26).  So the main term A_hi.B_hi and the 2^-11-smaller
 // correction terms accumulate in SEPARATE tensor-memory accumulators that meet in fp32 adds in the
-// epilogue, and chains are kept short: forward / dX reductions longer than 512 are chunked (launch()),
+// epilogue, and chains are kept short: forward / dX reductions longer than 768 are chunked (launch()),
 // the weight gradient folds its chains into a running fp32 sum every 16 K blocks.
 //
 // Two kernels (profiles/r01_gemm_kernels.md has the measurement behind every structural choice):
@@ -917,7 +917,7 @@ int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpos
 
 int64_t split_workspace_bytes(int K, int N) { return round_up(2LL * K * N * sizeof(float), 256); }
 
-static int g_max_chain_k = 512;                          // longest tensor-core accumulation chain of the forward / dX kernel
+static int g_max_chain_k = 768;                          // longest tensor-core accumulation chain of the forward / dX kernel
 void set_max_chain_k(int k) { if (k >= BK && k % BK == 0) g_max_chain_k = k; }
 
 // Bt: weights already split, laid out [N][K] (reduction contiguous): hi at Bt, lo at Bt + N*K.
@@ -938,8 +938,8 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
   // The tensor core adds every K = 8 step into the fp32 accumulator with TRUNCATION: a chain of n steps shrinks the
   // result by ~n * 2^-26 (measured 2e-5 on the BatchNorm variances of a hidden-512 model with K = 2048 in one chain;
   // with chains of 1024 one gradient tensor of that model was 1.4e-5 off the float64 oracle, with 512 all are inside
-  // max(1e-5, 4 x the error of a float32 CPU run)).  Longer reductions therefore run as chunks of <= 512 (64 steps)
-  // that meet in C through the epilogue's round-to-nearest reduce-add: +3% on the hidden-512 step.
+  // max(1e-5, 4 x the error of a float32 CPU run), with 768 as well).  Longer reductions therefore run as chunks of
+  // <= 768 (96 steps) that meet in C through the epilogue's round-to-nearest reduce-add.
   const int kMaxChainK = g_max_chain_k;
   for (int k0 = 0; k0 < K; k0 += kMaxChainK) {
     const int kc = K - k0 < kMaxChainK ? K - k0 : kMaxChainK;

@@ -25,7 +25,7 @@ for name, shape, off, buf in named_slices(cfg):
     n = int(np.prod(shape)); r = ref["grads"][off:off+n]
     e2[name] = np.abs(r2["grads"][off:off+n]-r).max()/max(np.abs(r).max(), floor)
 print("O2 worst", sorted(e2.items(), key=lambda kv: -kv[1])[:4])
-for chain_k, wchain in ((1024, 16), (512, 16), (256, 16)):
+for chain_k, wchain in ((768, 16), (512, 16)):
     _lib.load().gcs_debug_set_param(5, chain_k); _lib.load().gcs_debug_set_param(3, wchain)
     m = g.GeneralGNN(2, activation="softmax", hidden=512); m.build(32); m.load_flat(w, s)
     la, probs = m.train_step_grads([x, a, i], y)
