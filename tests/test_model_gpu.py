@@ -117,7 +117,11 @@ def test_forward_backward_hidden256_cfg1_slice(smooth):
     assert rel_err(host(model.state), ref["new_state"]) < TOL
     got = host(model.grads)
     if smooth:
-        assert_grads_close(got, ref["grads"], cfg)
+        # per tensor: 1e-5, or the float32 noise floor where that is higher - the biases in front of a BatchNorm have a
+        # mathematically zero gradient whose float32 evaluation (here and in the CPU restatement alike) is pure
+        # rounding noise of ~1e-5 of the floor
+        o2 = O2.loss_and_grads(cfg, block_specs(cfg), w, s, xr, idx[:, 0], idx[:, 1], seg, yr, 8)
+        assert_grads_close(got, ref["grads"], cfg, o2["grads"])
         assert rel_err(got, ref["grads"]) < TOL
     else:
         assert rel_err(got, ref["grads"]) < 5e-3
