@@ -338,7 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-graphs", type=int, default=B_GRAPHS)
-    ap.add_argument("--pool-batches", type=int, default=2, help="synthetic pool size in batches per rank")
+    ap.add_argument("--pool-batches", type=int, default=4, help="synthetic pool size in batches per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

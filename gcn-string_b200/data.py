@@ -424,7 +424,11 @@ class DisjointLoader:
             if self.shuffle:
                 np.random.shuffle(self._order)
             if self.shuffle or self._order_dev is None:
-                self._order_dev = torch.from_numpy(self._order.copy()).cuda()
+                # pinned staging + asynchronous copy: a pageable .cuda() blocks the host until the device has drained
+                # everything queued before it, once per epoch
+                staged = torch.from_numpy(self._order.copy()).pin_memory()
+                self._order_dev = staged.cuda(non_blocking=True)
+                self._order_staged = staged            # keep the pinned buffer alive until the copy has run
             order_host = self._order.copy()
             for b in range(self.steps_per_epoch):
                 start = b * self.batch_size
