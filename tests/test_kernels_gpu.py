@@ -141,6 +141,40 @@ def test_linear_forward_and_gradients(M, K, N):
     assert rel_err(host(acc), base + dH64 @ W64.T) < TOL
 
 
+@pytest.mark.parametrize("M,K,N", [(1, 256, 128), (255, 128, 256), (256, 512, 512), (257, 384, 128), (511, 2048, 256),
+                                   (33000, 1024, 256)])
+def test_tensor_core_gemms_forced(M, K, N):
+    """The tcgen05 kernels with the FFMA fallback disabled (mode 2 raises when the shape is not eligible): ragged row
+    counts around the 256-row CTA-pair tile, reductions chunked at 768, N = 128 / 512, both weight-gradient kernels
+    (CTA pair when K % 256 == 0, one CTA otherwise), strided operands, accumulate, run-to-run determinism."""
+    lib = _lib.load()
+    rng = np.random.default_rng(M * 7 + K + N)
+    wideA = rng.standard_normal((M, K + 64)).astype(np.float32)
+    A = wideA[:, 32:32 + K]                                  # lda = K + 64, 128-byte aligned start
+    W = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    dH = rng.standard_normal((M, N)).astype(np.float32)
+    A64, W64, dH64 = A.astype(np.float64), W.astype(np.float64), dH.astype(np.float64)
+    dA = dev(wideA)[:, 32:32 + K]
+    try:
+        lib.gcs_debug_set_gemm_mode(2)
+        out = torch.zeros(M, N + 128, device="cuda")
+        y = ops.linear_fwd(dA, dev(W), dev(b), out=out[:, 128:])          # ldc = N + 128
+        assert rel_err(host(y), A64 @ W64 + b) < TOL and float(out[:, :128].abs().max()) == 0.0
+        y2 = ops.linear_fwd(dA, dev(W), dev(b))
+        assert torch.equal(y2, y.contiguous())                              # deterministic, layout-independent
+        dW, _ = ops.linear_bwd_weight(dA, dev(dH), want_db=False)
+        assert rel_err(host(dW), A64.T @ dH64) < TOL
+        dW2, _ = ops.linear_bwd_weight(dA, dev(dH), want_db=False)
+        assert torch.equal(dW, dW2)
+        base = rng.standard_normal((M, K)).astype(np.float32)
+        acc = ops.linear_bwd_input(dev(dH), dev(W), out=dev(base), accumulate=True)
+        assert rel_err(host(acc), base + dH64 @ W64.T) < TOL
+        assert rel_err(host(ops.linear_bwd_input(dev(dH), dev(W))), dH64 @ W64.T) < TOL
+    finally:
+        lib.gcs_debug_set_gemm_mode(0)
+
+
 def test_linear_on_strided_views_of_the_concat_buffer():
     rng = np.random.default_rng(9)
     cat = dev(rng.standard_normal((500, 5 * 64)).astype(np.float32))
