@@ -171,7 +171,7 @@ def run_b200(args):
 
     def make(device_resident, shuffle):
         loader = g.DisjointLoader(ds, batch_size=B, epochs=None, shuffle=shuffle, symmetric=True,
-                                  device_resident=device_resident)
+                                  device_resident=device_resident)      # each rank owns its pool: shards are per-rank here
         model = g.GeneralGNN(CLASSES, activation="softmax", hidden=HIDDEN, message_passing=LAYERS, seed=0)
         model.build(N_FEAT)
         trainer = DataParallelTrainer(model, g.optimizers.SGD(learning_rate=sched))

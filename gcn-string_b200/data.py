@@ -358,7 +358,7 @@ class DisjointLoader:
     """
 
     def __init__(self, dataset, node_level=False, batch_size=1, epochs=None, shuffle=True, rank=0, world_size=1,
-                 want_coo=False, symmetric=None, device_resident=True, prefetch=None):
+                 want_coo=False, symmetric=None, device_resident=True, prefetch=None, balance=None):
         if node_level:
             raise NotImplementedError("node_level=True labels are not built (reference uses graph labels)")
         packed = dataset if isinstance(dataset, PackedGraphs) else pack_graphs(list(dataset))
@@ -374,6 +374,11 @@ class DisjointLoader:
         self.epochs = epochs
         self.shuffle = shuffle
         self.rank, self.world_size = int(rank), int(world_size)
+        if balance not in (None, "count", "nnz"):
+            raise ValueError("balance must be None, 'count' or 'nnz'")
+        # 'nnz': shards of a global batch are balanced by stored entries + nodes (distributed.balanced_shard) instead
+        # of being contiguous runs of equal graph count
+        self.balance = None if balance == "count" else balance
         self.want_coo = want_coo
         # one batch ahead on a side stream: the H2D upload (host-resident store) and the batching
         # kernels of step t+1 overlap the training step t
@@ -436,7 +441,14 @@ class DisjointLoader:
                 lo, hi = self._slices_of_rank(start, stop)
                 if hi <= lo:
                     raise RuntimeError("a data-parallel rank received an empty shard; use batch_size >= world_size")
-                yield self._order_dev[lo:hi], order_host[lo:hi], stop - start
+                if self.balance == "nnz" and self.world_size > 1:
+                    from .distributed import balanced_shard
+                    ids = order_host[start:stop]
+                    cost = self.store.h_n_edges[ids] + 4 * self.store.h_n_nodes[ids]
+                    mine = np.ascontiguousarray(balanced_shard(ids, cost, self.rank, self.world_size))
+                    yield torch.from_numpy(mine).pin_memory().cuda(non_blocking=True), mine, stop - start
+                else:
+                    yield self._order_dev[lo:hi], order_host[lo:hi], stop - start
 
     def _launch(self, item, stream):
         """Enqueue upload + batching kernels for one step on `stream`."""

@@ -38,6 +38,36 @@ def shard_bounds(start: int, stop: int, rank: int, world_size: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def balanced_shard(ids, cost, rank: int, world_size: int):
+    """The part of a global batch owned by ``rank`` when shards are balanced by WORK instead of graph
+    count (step time ~ nodes*H^2 + nnz*H, protein lengths are log-normal).  ``ids`` are the
+    graph ids of the batch, ``cost`` their work estimates (same length).  Deterministic and identical on
+    every rank: longest-processing-time greedy - graphs in descending cost (ties by position) go to the
+    least-loaded rank that still has room (ties to the lowest rank).  Shard sizes are those of
+    ``shard_bounds`` (they differ by at most one graph, which keeps the 1/global_batch scaling and the
+    per-rank BatchNorm sample sizes as in the contiguous split); order inside a shard follows the batch."""
+    import heapq
+    import numpy as np
+    ids = np.asarray(ids)
+    cost = np.asarray(cost)
+    n = ids.shape[0]
+    if world_size == 1:
+        return ids
+    room = [shard_bounds(0, n, r, world_size)[1] - shard_bounds(0, n, r, world_size)[0] for r in range(world_size)]
+    heap = [(0, r) for r in range(world_size) if room[r] > 0]
+    heapq.heapify(heap)
+    mine = []
+    for k in np.argsort(-cost, kind="stable").tolist():
+        load, r = heapq.heappop(heap)
+        if r == rank:
+            mine.append(k)
+        room[r] -= 1
+        if room[r] > 0:
+            heapq.heappush(heap, (load + int(cost[k]), r))
+    mine.sort()
+    return ids[np.asarray(mine, dtype=np.int64)]
+
+
 def allreduce_gradients(flat_grads, group=None):
     """In-place SUM all-reduce of the flat gradient bucket (no-op for a single process)."""
     import torch.distributed as dist

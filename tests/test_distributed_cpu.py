@@ -81,3 +81,25 @@ def test_shard_bounds_tile_the_batch():
         assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
         sizes = [hi - lo for lo, hi in parts]
         assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+def test_balanced_shards_partition_the_batch_and_even_out_the_work():
+    """§8e: shards balanced by work.  Every graph on exactly one rank, the same shard sizes as the contiguous
+    split, identical result on every rank, and a smaller spread of per-rank work on log-normal graph sizes."""
+    sys.path.insert(0, ROOT)
+    from gcn_string_b200 import distributed as gd
+    rng = np.random.default_rng(0)
+    for n, world in [(1024, 8), (1000, 8), (7, 2), (5, 4), (64, 1)]:
+        ids = rng.permutation(10 * n)[:n]
+        cost = np.rint(rng.lognormal(8.0, 0.5, n)).astype(np.int64)
+        parts = [gd.balanced_shard(ids, cost, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == sorted(ids.tolist())
+        want_sizes = [gd.shard_bounds(0, n, r, world)[1] - gd.shard_bounds(0, n, r, world)[0] for r in range(world)]
+        assert [len(p) for p in parts] == want_sizes
+        again = [gd.balanced_shard(ids, cost, r, world) for r in range(world)]
+        assert all(np.array_equal(a, b) for a, b in zip(parts, again))
+        if n >= 1000:
+            lookup = dict(zip(ids.tolist(), cost.tolist()))
+            work = np.array([sum(lookup[i] for i in p.tolist()) for p in parts], dtype=np.float64)
+            contiguous = np.array([cost[slice(*gd.shard_bounds(0, n, r, world))].sum() for r in range(world)], dtype=np.float64)
+            assert work.max() / work.mean() < 1.002 < contiguous.max() / contiguous.mean()

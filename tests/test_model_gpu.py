@@ -377,3 +377,21 @@ def test_forward_backward_hidden512_cfg5_shape():
     p_inf = model([x, a, i], training=False)
     ref_inf, _ = O1.forward(cfg, block_specs(cfg), w, s, xr, idx[:, 0], idx[:, 1], seg, 3, training=False)
     assert rel_err(host(p_inf), ref_inf) < TOL
+
+
+def test_loader_work_balanced_shards():
+    """DisjointLoader(balance='nnz'): the ranks' batches partition every global batch, with the shard sizes of the
+    contiguous split, and carry the global batch size for the 1/global_batch gradient scaling."""
+    ds = synthetic.make_dataset(23, seed=31, n_mean=60, deg=8, n_feat=4)
+    parts = []
+    for r in range(3):
+        ld = g.DisjointLoader(ds, batch_size=10, epochs=1, shuffle=False, rank=r, world_size=3, balance="nnz")
+        parts.append([(host(y), a.nnz, a.global_batch_graphs) for (_, a, _), y in ld])
+    assert [len(p) for p in parts] == [3, 3, 3]
+    for step, (lo, hi) in enumerate([(0, 10), (10, 20), (20, 23)]):
+        ys = np.concatenate([parts[r][step][0] for r in range(3) if parts[r][step][0].shape[0]])
+        assert ys.shape[0] == hi - lo and all(parts[r][step][2] == hi - lo for r in range(3))
+        assert sorted(map(tuple, ys.tolist())) == sorted(map(tuple, ds.y[lo:hi].tolist()))
+        assert sum(parts[r][step][1] for r in range(3)) == int(ds.n_edges[lo:hi].sum())
+    nnz = [parts[r][0][1] for r in range(3)]
+    assert max(nnz) - min(nnz) <= int(ds.n_edges[:10].max())
