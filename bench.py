@@ -142,7 +142,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "sample_graphs_per_step": n},
             "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -325,13 +325,32 @@ def run_b200(args):
         "edges_per_sec_train_step": world * nnz / (ms_step / 1e3),
         "ops": ops_report,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else any library writes to file descriptor 1 (NCCL's version
+    banner lands there on some launches) is sent to stderr for the duration of the run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
