@@ -174,7 +174,7 @@ def run_b200(args):
                                   device_resident=device_resident)      # each rank owns its pool: shards are per-rank here
         model = g.GeneralGNN(CLASSES, activation="softmax", hidden=HIDDEN, message_passing=LAYERS, seed=0)
         model.build(N_FEAT)
-        trainer = DataParallelTrainer(model, g.optimizers.SGD(learning_rate=sched))
+        trainer = DataParallelTrainer(model, g.optimizers.SGD(learning_rate=sched), sync_bn=args.sync_bn)
         return loader, model, trainer
 
     def barrier():
@@ -311,7 +311,8 @@ def run_b200(args):
                    "nnz_per_step_per_gpu": nnz, "optimizer": "SGD PiecewiseConstantDecay (gcn.py:321-325)",
                    "parallelism": f"graph-sharded data parallel x{world}, one flat NCCL all-reduce (4.26 MB)/step",
                    "l2": "activations per step (cat 2.6 GB, h 0.5 GB/layer) far exceed the 126 MB L2; batches reshuffled "
-                         "every step", "bn": "replica-local BatchNorm statistics"},
+                         "every step", "bn": ("synchronised BatchNorm statistics (16 extra fp64 all-reduces of <= 3H+1 values per step)"
+                          if args.sync_bn and world > 1 else "replica-local BatchNorm statistics")},
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(io["h2d"]),
                 "d2h_bytes_per_step": 8, "note": "dataset in pinned host memory; per step: H2D of the batch's packed "
                 "graphs, device batching, train step, D2H of {loss, acc}"},
@@ -359,6 +360,8 @@ def main():
     ap.add_argument("--batch-graphs", type=int, default=B_GRAPHS)
     ap.add_argument("--pool-batches", type=int, default=4, help="synthetic pool size in batches per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true", help="all-reduce the BatchNorm statistics too (a G-GPU step then "
+                    "equals one step on the union batch); off by default: the gradient all-reduce is the only collective")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     return run_reference(args) if args.impl == "reference" else run_b200(args)

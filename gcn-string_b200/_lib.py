@@ -40,6 +40,7 @@ PROTOTYPES = {
     "gcs_version": (c_int32, []),
     "gcs_last_error": (c_char_p, []),
     "gcs_device_sm_count": (c_int32, []),
+    "gcs_set_allreduce_hook": (c_int32, [P, P, I32]),
     "gcs_batch_disjoint": (c_int32, [P, P, P, P, P, I32, I32, P, I32, I64, I64, P, P, P, P, P, P, P, P, P, P]),
     "gcs_coo_to_csr": (c_int32, [P, I64, I64, P, P, P, P]),
     "gcs_segment_ptr": (c_int32, [P, I64, I32, P, P, P]),
@@ -145,6 +146,36 @@ def model_config(cfg) -> ModelConfig:
     return ModelConfig(cfg.in_features, cfg.output, cfg.hidden, cfg.message_passing, cfg.pre_process,
                        cfg.post_process, CONNECTIVITY[cfg.connectivity], POOL[cfg.pool],
                        FINAL_ACT[cfg.activation], cfg.bn_momentum, cfg.bn_epsilon)
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int32, c_void_p, c_int64, c_void_p, c_void_p)
+_hook_keepalive = {}
+
+
+def set_allreduce_hook(fn, world_size: int = 1):
+    """Install (or, with ``fn=None``, remove) the synchronised-BatchNorm hook of the calling thread.
+    ``fn(device_ptr: int, n_doubles: int, stream: int) -> None`` must sum the fp64 buffer over all ranks in
+    place, enqueued on ``stream``; exceptions are reported as a failed status of the native call."""
+    import threading
+    lib = load()
+    key = threading.get_ident()
+    if fn is None:
+        check(lib.gcs_set_allreduce_hook(None, None, 1), "gcs_set_allreduce_hook")
+        _hook_keepalive.pop(key, None)
+        return
+
+    def trampoline(buf, n, stream, _user):
+        try:
+            fn(int(buf), int(n), int(stream or 0))
+            return 0
+        except Exception:                          # never let an exception cross the C frames
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    cfn = ALLREDUCE_FN(trampoline)
+    _hook_keepalive[key] = cfn                     # the C side keeps a raw pointer to it
+    check(lib.gcs_set_allreduce_hook(ctypes.cast(cfn, c_void_p), None, int(world_size)), "gcs_set_allreduce_hook")
 
 
 def profile_begin():

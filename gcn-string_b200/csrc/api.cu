@@ -103,4 +103,20 @@ extern "C" int gcs_debug_profile_end(char* out, int cap) {
 
 extern "C" int gcs_version(void) { return 100; }   // 0.1.0
 extern "C" const char* gcs_last_error(void) { return gcs::error_buffer(); }
+
+namespace gcs {
+SyncHook& sync_hook() {
+  static thread_local SyncHook h;
+  return h;
+}
+}  // namespace gcs
+
+extern "C" int gcs_set_allreduce_hook(gcs_allreduce_fn fn, void* user, int32_t world_size) {
+  if (fn && world_size < 1) return gcs::fail(GCS_ERR_INVALID_ARGUMENT, "gcs_set_allreduce_hook: world_size must be >= 1");
+  gcs::SyncHook& h = gcs::sync_hook();
+  h.fn = fn;
+  h.user = user;
+  h.world = fn ? world_size : 1;
+  return GCS_OK;
+}
 extern "C" int gcs_device_sm_count(void) { return gcs::sm_count(); }

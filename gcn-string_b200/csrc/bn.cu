@@ -131,6 +131,38 @@ __global__ void __launch_bounds__(256) bn_stats_final_kernel(const double* __res
   }
 }
 
+// Synchronised BatchNorm: the per-column sums of this rank (+ its row count as the last element) go through the
+// all-reduce hook, mean / variance are formed from the global sums.
+__global__ void __launch_bounds__(256) bn_stats_sums_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
+                                                            double* __restrict__ sums) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = lane; k < splits; k += 32) {
+    s += ws[(static_cast<int64_t>(k) * C + c) * 2];
+    q += ws[(static_cast<int64_t>(k) * C + c) * 2 + 1];
+  }
+  s = warp_sum_fixed(s);
+  q = warp_sum_fixed(q);
+  if (lane == 0) {
+    sums[c] = s;
+    sums[C + c] = q;
+    if (c == 0) sums[2 * C] = static_cast<double>(M);
+  }
+}
+
+__global__ void bn_stats_finish_kernel(const double* __restrict__ sums, int C, float* __restrict__ mean,
+                                       float* __restrict__ var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double Mg = sums[2 * C];
+  const double m = sums[c] / Mg;
+  double v = sums[C + c] / Mg - m * m;
+  if (v < 0.0) v = 0.0;
+  mean[c] = static_cast<float>(m);
+  var[c] = static_cast<float>(v);
+}
+
 __global__ void bn_fold_kernel(const float* __restrict__ mean, const float* __restrict__ var,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float eps, float momentum, float* __restrict__ moving_mean,
@@ -298,6 +330,45 @@ __global__ void __launch_bounds__(256) bn_bwd_final_kernel(const double* __restr
   coef[4 * c + 3] = gamma[c] * rs;
 }
 
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
+                                                          double* __restrict__ sums) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int k = lane; k < splits; k += 32) {
+    const double* p = ws + (static_cast<int64_t>(k) * C + c) * 3;
+    s1 += p[0]; s2 += p[1]; s3 += p[2];
+  }
+  s1 = warp_sum_fixed(s1);
+  s2 = warp_sum_fixed(s2);
+  s3 = warp_sum_fixed(s3);
+  if (lane == 0) {
+    sums[c] = s1;
+    sums[C + c] = s2;
+    sums[2 * C + c] = s3;
+    if (c == 0) sums[3 * C] = static_cast<double>(M);
+  }
+}
+
+// From GLOBAL sums: the parameter gradients are divided by the world size because the caller's SUM all-reduce of the
+// flat gradient buffer adds the (identical) values of all ranks up again.
+__global__ void bn_bwd_finish_kernel(const double* __restrict__ sums, int C, double inv_world, const float* __restrict__ var,
+                                     const float* __restrict__ gamma, float eps, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, float* __restrict__ dalpha, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double Mg = sums[3 * C];
+  const double s1 = sums[c], s2 = sums[C + c], s3 = sums[2 * C + c];
+  if (dbeta) dbeta[c] = static_cast<float>(s1 * inv_world);
+  if (dgamma) dgamma[c] = static_cast<float>(s2 * inv_world);
+  if (dalpha) dalpha[c] = static_cast<float>(s3 * inv_world);
+  const float rs = __frsqrt_rn(var[c] + eps);
+  coef[4 * c] = static_cast<float>(s1 / Mg);
+  coef[4 * c + 1] = static_cast<float>(s2 / Mg);
+  coef[4 * c + 2] = rs;
+  coef[4 * c + 3] = gamma[c] * rs;
+}
+
 // Backward pass 2: dh = gamma*rstd*(dz - S1/M - xhat*S2/M).  Same thread->column mapping as the
 // reduction pass (lane = VEC columns, 8 row warps per block, grid.y row splits), so the per-column
 // coefficients stay in registers for the whole row loop.
@@ -412,7 +483,7 @@ static inline int64_t elementwise_blocks(int64_t work) {
 extern "C" int64_t gcs_bn_workspace_bytes(int64_t M, int32_t C) {
   if (M < 0 || C <= 0) return 0;
   return round_up(bn_max_splits(M) * C * 3 * static_cast<int64_t>(sizeof(double)), 256) +
-         round_up(4LL * C * sizeof(float), 256);
+         round_up(4LL * C * sizeof(float), 256) + round_up((3LL * C + 1) * sizeof(double), 256);   // partials | coef | sync sums
 }
 
 extern "C" int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, float* mean, float* var,
@@ -430,6 +501,18 @@ extern "C" int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, f
   if (vec) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
   else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
   GCS_CHECK_LAUNCH("bn_stats_partial_kernel");
+  const SyncHook& hook = sync_hook();
+  if (hook.fn) {
+    double* sums = reinterpret_cast<double*>(static_cast<char*>(workspace) +
+                                             round_up(bn_max_splits(M) * C * 3 * static_cast<int64_t>(sizeof(double)), 256) +
+                                             round_up(4LL * C * sizeof(float), 256));
+    bn_stats_sums_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, sums);
+    GCS_CHECK_LAUNCH("bn_stats_sums_kernel");
+    if (hook.fn(sums, 2LL * C + 1, stream, hook.user) != 0) return fail(GCS_ERR_CUDA, "gcs_bn_stats: the all-reduce hook failed");
+    bn_stats_finish_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(sums, C, mean, var);
+    GCS_CHECK_LAUNCH("bn_stats_finish_kernel");
+    return GCS_OK;
+  }
   bn_stats_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, mean, var);
   GCS_CHECK_LAUNCH("bn_stats_final_kernel");
   return GCS_OK;
@@ -483,8 +566,18 @@ extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, i
   if (vec) bn_bwd_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
   else bn_bwd_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, var, gamma, beta, alpha, eps, M, C, g.rows_per_split, ws);
   GCS_CHECK_LAUNCH("bn_bwd_partial_kernel");
-  bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, var, gamma, eps, dgamma, dbeta, dalpha, coef);
-  GCS_CHECK_LAUNCH("bn_bwd_final_kernel");
+  const SyncHook& hook = sync_hook();
+  if (hook.fn) {
+    double* sums = reinterpret_cast<double*>(reinterpret_cast<char*>(coef) + round_up(4LL * C * sizeof(float), 256));
+    bn_bwd_sums_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, sums);
+    GCS_CHECK_LAUNCH("bn_bwd_sums_kernel");
+    if (hook.fn(sums, 3LL * C + 1, stream, hook.user) != 0) return fail(GCS_ERR_CUDA, "gcs_bn_prelu_bwd: the all-reduce hook failed");
+    bn_bwd_finish_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(sums, C, 1.0 / hook.world, var, gamma, eps, dgamma, dbeta, dalpha, coef);
+    GCS_CHECK_LAUNCH("bn_bwd_finish_kernel");
+  } else {
+    bn_bwd_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, var, gamma, eps, dgamma, dbeta, dalpha, coef);
+    GCS_CHECK_LAUNCH("bn_bwd_final_kernel");
+  }
   double* cws = dbias ? ws : nullptr;          // the reduction partials are consumed: reuse their space
   if (vec) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);
   else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);

@@ -20,6 +20,14 @@ int sm_count();
 
 int exclusive_scan_i32(const int32_t* cnt, int64_t n, int32_t* out, cudaStream_t st);   // batching.cu
 
+// Synchronised-BatchNorm hook (gcs_set_allreduce_hook), per host thread.
+struct SyncHook {
+  gcs_allreduce_fn fn = nullptr;
+  void* user = nullptr;
+  int world = 1;
+};
+SyncHook& sync_hook();
+
 // Count of kernel launches issued by this library (bench.py's `gpu_launches`).
 void count_launch();
 

@@ -84,13 +84,46 @@ def broadcast_parameters(model, src: int = 0, group=None):
         dist.broadcast(model.state, src=src, group=group)
 
 
+def sync_batchnorm_hook(model, group=None):
+    """The all-reduce callback of synchronised BatchNorm for ``model``: sums the per-column fp64 statistics the
+    native BatchNorm kernels leave in the model's workspace over all ranks (torch.distributed, on the stream the
+    step runs on).  Returns ``fn(device_ptr, n_doubles, stream)`` for ``_lib.set_allreduce_hook``."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(ptr, n, stream):
+        ws = model._ws
+        off = ptr - ws.data_ptr() if ws is not None else -1
+        if off < 0 or off + 8 * n > ws.numel():
+            raise RuntimeError("sync-BatchNorm buffer is not inside the model workspace")
+        dist.all_reduce(ws[off:off + 8 * n].view(torch.float64), op=dist.ReduceOp.SUM, group=group)
+    return fn
+
+
 class DataParallelTrainer:
     """train_step = local fused forward/backward (grad_scale = 1/global_batch) -> one flat
-    all-reduce -> fused optimizer step, identical on every rank."""
+    all-reduce -> fused optimizer step, identical on every rank.
 
-    def __init__(self, model, optimizer, group=None):
+    ``sync_bn=True`` additionally all-reduces the BatchNorm statistics (2H+1 doubles per layer in the forward,
+    3H+1 in the backward): the step then equals ONE single-device step on the union of the shards - same loss
+    gradient, same BatchNorm state on every rank - instead of a count-weighted average of per-shard steps."""
+
+    def __init__(self, model, optimizer, group=None, sync_bn: bool = False):
         self.model, self.optimizer, self.group = model, optimizer, group
+        self.sync_bn = bool(sync_bn)
         self._synced = False
+
+    def _hooked(self, fn):
+        """Run ``fn`` with the sync-BatchNorm hook installed (no-op for one process or sync_bn=False)."""
+        from . import _lib
+        _, ws = world()
+        if not self.sync_bn or ws == 1:
+            return fn()
+        _lib.set_allreduce_hook(sync_batchnorm_hook(self.model, self.group), ws)
+        try:
+            return fn()
+        finally:
+            _lib.set_allreduce_hook(None)
 
     def train_step(self, inputs, target, global_batch: Optional[int] = None):
         rank, ws = world()
@@ -100,11 +133,12 @@ class DataParallelTrainer:
         a = inputs[1]
         if global_batch is None:
             global_batch = getattr(a, "global_batch_graphs", None) or target.shape[0] * ws
-        loss_acc, probs = self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch))
+        step = lambda: self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch))   # noqa: E731
+        loss_acc, probs = self._hooked(step)
         if not self._synced:                      # first call built the model lazily
             broadcast_parameters(self.model, 0, self.group)
             self._synced = True
-            loss_acc, probs = self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch))
+            loss_acc, probs = self._hooked(step)
         allreduce_gradients(self.model.grads, self.group)
         self.optimizer.apply_flat(self.model.params, self.model.grads)
         return loss_acc, probs

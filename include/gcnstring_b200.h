@@ -45,6 +45,17 @@ const char* gcs_last_error(void);
 /* SM count of the current device (grid sizing); <0 on error. */
 int gcs_device_sm_count(void);
 
+/* Optional synchronised BatchNorm for data-parallel runs (SURVEY.md 8e lists it as the variant in which a G-GPU
+ * step equals ONE reference step on the union of the shards).  While a hook is installed (per host thread),
+ * gcs_bn_stats and gcs_bn_prelu_bwd - and therefore the model entry points - hand their per-column fp64 sums
+ * (sum h, sum h^2 | sum dz, sum dz*xhat, sum da*min(z,0), then the local row count as the last element) to `fn`,
+ * which must SUM the `n` doubles at `device_buf` over all ranks, in place, enqueued on `stream`; mean / variance and
+ * the gradient coefficients are then formed from the global sums and the global row count.  dgamma / dbeta / dalpha
+ * are written as (global sum) / world_size so that the caller's SUM all-reduce of the flat gradient buffer restores
+ * them.  fn == NULL removes the hook (the default: replica-local statistics, gradient all-reduce only). */
+typedef int (*gcs_allreduce_fn)(double* device_buf, int64_t n, gcs_stream stream, void* user);
+int gcs_set_allreduce_hook(gcs_allreduce_fn fn, void* user, int32_t world_size);
+
 /* ---------------------------------------------------------------------------------
  * K0  Disjoint batching on the device.
  * Replaces spektral.data.DisjointLoader.collate as driven by src/scripts/gcn.py:316-317,

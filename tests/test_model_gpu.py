@@ -395,3 +395,73 @@ def test_loader_work_balanced_shards():
         assert sum(parts[r][step][1] for r in range(3)) == int(ds.n_edges[lo:hi].sum())
     nnz = [parts[r][0][1] for r in range(3)]
     assert max(nnz) - min(nnz) <= int(ds.n_edges[:10].max())
+
+
+def test_sync_batchnorm_two_ranks_equal_one_step_on_the_union(small_case):
+    """Synchronised BatchNorm (gcs_set_allreduce_hook): two replicas, each on its shard of the batch, with their
+    BatchNorm sums all-reduced, reproduce ONE oracle step on the union - summed gradients, BatchNorm state on both
+    replicas and the count-weighted loss.  The two ranks are two host threads with their own CUDA streams on this one
+    GPU; the all-reduce is played by a barrier + add (NCCL itself cannot run two ranks on one device)."""
+    import threading
+    from gcn_string_b200 import _lib
+    c = small_case
+    cfg, ds = c["cfg"], c["ds"]
+    ref = O1.loss_and_grads(cfg, c["specs"], c["w"], c["s"], c["x"], c["idx"][:, 0], c["idx"][:, 1], c["seg"], c["y"], 8)
+    shards = [(0, 5), (5, 8)]                                 # unequal shards
+    models = [make_model(cfg, c["w"], c["s"]) for _ in range(2)]
+    barrier = threading.Barrier(2)
+    pending = [None, None]
+    out, errors = [None, None], []
+
+    def view(model, ptr, n):
+        off = ptr - model._ws.data_ptr()
+        return model._ws[off:off + 8 * n].view(torch.float64)
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                lo, hi = shards[r]
+                ids = np.arange(lo, hi, dtype=np.int64)
+                x, a, seg, y = g.data.DeviceGraphStore(ds).batch(torch.from_numpy(ids).cuda(), ids)
+
+                def allreduce(ptr, n, _stream):
+                    stream.synchronize()                      # my sums are complete
+                    pending[r] = (ptr, n)
+                    barrier.wait()
+                    mine, other = view(models[r], *pending[r]), view(models[1 - r], *pending[1 - r])
+                    total = mine + other
+                    stream.synchronize()                      # both ranks have read before either overwrites
+                    barrier.wait()
+                    mine.copy_(total)
+
+                _lib.set_allreduce_hook(allreduce, 2)
+                try:
+                    loss_acc, probs = models[r].train_step_grads([x, a, seg], y, grad_scale=1.0 / 8)
+                finally:
+                    _lib.set_allreduce_hook(None)
+                stream.synchronize()
+                out[r] = (host(loss_acc), host(probs), host(models[r].grads), host(models[r].state), hi - lo)
+        except Exception as e:                                # surface failures of either thread
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    [t.start() for t in threads]
+    [t.join(120) for t in threads]
+    assert not errors, errors
+    grads = out[0][2].astype(np.float64) + out[1][2].astype(np.float64)        # the flat gradient all-reduce
+    o2 = O2.loss_and_grads(cfg, c["specs"], c["w"], c["s"], c["x"], c["idx"][:, 0], c["idx"][:, 1], c["seg"], c["y"], 8)
+    assert_grads_close(grads, ref["grads"], cfg, o2["grads"])
+    for r in range(2):
+        assert rel_err(out[r][3], ref["new_state"]) < TOL                       # identical BatchNorm state on both ranks
+    assert rel_err(np.concatenate([out[0][1], out[1][1]]), ref["probs"]) < TOL
+    loss = sum(out[r][0][0] * out[r][4] for r in range(2)) / 8.0
+    assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"])
+    # without the hook the same shards give replica-local statistics: a different (shard-wise) step
+    plain = make_model(cfg, c["w"], c["s"])
+    ids = np.arange(0, 5, dtype=np.int64)
+    x, a, seg, y = g.data.DeviceGraphStore(ds).batch(torch.from_numpy(ids).cuda(), ids)
+    plain.train_step_grads([x, a, seg], y, grad_scale=1.0 / 8)
+    assert rel_err(host(plain.state), ref["new_state"]) > 1e-4
