@@ -60,6 +60,7 @@ PROTOTYPES = {
     "gcs_spmm_rb4_workspace_bytes": (c_int64, [I64]),
     "gcs_spmm_build_rb4": (c_int32, [P, P, I64, I64, P, P, P, I64, P]),
     "gcs_spmm_sum": (c_int32, [P, P, P, P, I64, P, I64, P, P, P, P, I64, I32, P]),
+    "gcs_spmm_aggregate": (c_int32, [P, P, P, P, P, I64, P, I64, P, P, P, P, I64, P, I64, I32, I32, P]),
     "gcs_segment_sum_fwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_segment_sum_bwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_softmax_xent": (c_int32, [P, P, I32, I32, P, P, P, F32, P]),

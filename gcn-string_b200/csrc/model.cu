@@ -16,6 +16,10 @@
 // the gradient of one H-wide block of `cat` is then ONE long-K GEMM over all its consumers
 // (trailing columns of dhcat x the matching row blocks of their kernels) with the pooled
 // gradient broadcast fused into the epilogue - no read-modify-write of a concat-wide buffer.
+// connectivity = 'sum' (out = z + out, Keras Add) and None (out = z) keep every layer H wide: the L+1 node
+// embeddings out_0..out_L live as L+1 separate [N, H] slabs of the same `cat` allocation (each is the GEMM input of the
+// next layer and is needed again for its weight gradient), the skip operand is added in the aggregation's epilogue, and
+// the backward carries ONE running gradient g[N, H] = dLoss/d(out_k) that the input-gradient GEMM accumulates into.
 // The caller owns the workspace; nothing is allocated here.
 #include <vector>
 
@@ -54,8 +58,9 @@ static void build_blocks(const gcs_model_config& c, std::vector<BlockDesc>& out)
   };
   int k = c.in_features;
   for (int j = 0; j < c.pre_process; ++j) { push(k, c.hidden, true); k = c.hidden; }
-  for (int j = 0; j < c.message_passing; ++j) push(c.hidden * (j + 1), c.hidden, true);
-  k = c.hidden * (c.message_passing + 1);
+  const bool cat = c.connectivity == 1;
+  for (int j = 0; j < c.message_passing; ++j) push(cat ? c.hidden * (j + 1) : c.hidden, c.hidden, true);
+  k = cat ? c.hidden * (c.message_passing + 1) : c.hidden;
   for (int j = 0; j < c.post_process; ++j) {
     const bool last = j == c.post_process - 1;
     push(k, last ? c.output : c.hidden, !last);
@@ -69,7 +74,8 @@ static int check_config(const gcs_model_config* c) {
     return fail(GCS_ERR_INVALID_ARGUMENT, "model config: feature widths must be positive");
   if (c->message_passing < 1 || c->pre_process < 1 || c->post_process < 1)
     return fail(GCS_ERR_UNSUPPORTED, "model config: pre_process, message_passing, post_process must be >= 1");
-  if (c->connectivity != 1) return fail(GCS_ERR_UNSUPPORTED, "model config: only connectivity='cat' is built");
+  if (c->connectivity < 0 || c->connectivity > 2)
+    return fail(GCS_ERR_INVALID_ARGUMENT, "model config: connectivity must be 0 (None), 1 ('cat') or 2 ('sum')");
   if (c->pool != 0 && c->pool != 1) return fail(GCS_ERR_UNSUPPORTED, "model config: pool must be 'sum' or None");
   if (c->final_activation != 0 && c->final_activation != 1)
     return fail(GCS_ERR_UNSUPPORTED, "model config: final activation must be linear or softmax");
@@ -133,12 +139,12 @@ struct Plan {
 static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training, void* ws, Plan& p, int64_t* total) {
   build_blocks(c, p.blocks);
   p.P = c.pre_process; p.L = c.message_passing; p.Q = c.post_process;
-  p.H = c.hidden; p.Wc = c.hidden * (c.message_passing + 1); p.C = c.output;
+  p.H = c.hidden; p.Wc = c.connectivity == 1 ? c.hidden * (c.message_passing + 1) : c.hidden; p.C = c.output;
   p.N = N; p.B = B;
   p.rows_post = c.pool ? B : N;
   Arena a(ws);
   const int64_t NH = N * p.H;
-  p.cat = a.take<float>(N * p.Wc);
+  p.cat = a.take<float>(NH * (p.L + 1));         // 'cat': one [N, H(L+1)] matrix; otherwise L+1 slabs [N, H]
   p.h.assign(p.P + p.L, nullptr);
   if (training) {
     for (auto& q : p.h) q = a.take<float>(NH);
@@ -170,7 +176,7 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
   }
   p.bn_ws_bytes = bn_bytes;
   p.bn_ws = a.take<char>(bn_bytes);
-  int64_t lin_bytes = gcs_linear_workspace_bytes(N, p.L * p.H, p.H);     // concatenated input-gradient GEMM
+  int64_t lin_bytes = c.connectivity == 1 ? gcs_linear_workspace_bytes(N, p.L * p.H, p.H) : 0;   // concatenated input-gradient GEMM
   for (const auto& b : p.blocks) {
     const int64_t v = gcs_linear_workspace_bytes(N, b.k_in, b.m_out);
     if (v > lin_bytes) lin_bytes = v;
@@ -179,7 +185,7 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
   p.lin_ws = a.take<char>(lin_bytes);
   if (training) {
     if (!c.pool) p.gcat = a.take<float>(N * p.Wc);
-    p.dhcat = a.take<float>(NH * p.L);
+    p.dhcat = a.take<float>(c.connectivity == 1 ? NH * p.L : NH);
     p.tmp_a = a.take<float>(NH);
     p.tmp_b = a.take<float>(NH);
     p.tmp_c = a.take<float>(NH);
@@ -242,6 +248,10 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
                        const gcs_batch& bt, bool training, gcs_stream st) {
   const int H = p.H, Wc = p.Wc, L = p.L, P = p.P;
   const int64_t N = p.N;
+  const bool cat = c.connectivity == 1;
+  // out_k, the node embedding after k conv layers: the trailing (k+1)H columns of `cat`, or slab k
+  auto emb = [&](int k) { return cat ? p.cat + static_cast<int64_t>(L - k) * H : p.cat + static_cast<int64_t>(k) * N * H; };
+  const int64_t ld_emb = cat ? Wc : H;
   // pre-processing MLP
   const float* in = bt.x;
   int64_t ld_in = bt.ldx;
@@ -249,8 +259,8 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     const BlockDesc& b = p.blocks[j];
     GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
-    float* out = j < P - 1 ? p.act[j] : p.cat + static_cast<int64_t>(L) * H;
-    const int64_t ld_out = j < P - 1 ? H : Wc;
+    float* out = j < P - 1 ? p.act[j] : emb(0);
+    const int64_t ld_out = j < P - 1 ? H : ld_emb;
     const float* scale = p.stat[j] + 2 * H;
     GCS_TIMED("bn_prelu_fwd", gcs_bn_prelu_fwd(p.h[j], H, scale, scale + H, params + b.alpha(), out, ld_out, N, H, st));
     in = out;
@@ -260,19 +270,20 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
   for (int k = 0; k < L; ++k) {
     const int bi = P + k;
     const BlockDesc& b = p.blocks[bi];
-    const float* cin = p.cat + static_cast<int64_t>(L - k) * H;          // trailing (k+1)*H columns
-    GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, Wc, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
+    const float* cin = emb(k);
+    GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, ld_emb, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
     const float* scale = p.stat[bi] + 2 * H;
-    GCS_TIMED("spmm_fwd", gcs_spmm_sum(bt.rowptr, bt.colidx, bt.rb4_blk_ptr, bt.rb4_ent, N,
-                                       p.h[bi], H, scale, scale + H, params + b.alpha(),
-                                       p.cat + static_cast<int64_t>(L - k - 1) * H, Wc, H, st));
+    // z_k is the leading block of out_{k+1} ('cat'), or out_{k+1} = z_k (+ out_k for 'sum') in the next slab
+    GCS_TIMED("spmm_fwd", gcs_spmm_aggregate(bt.rowptr, bt.colidx, nullptr, bt.rb4_blk_ptr, bt.rb4_ent, N,
+                                             p.h[bi], H, scale, scale + H, params + b.alpha(),
+                                             c.connectivity == 2 ? emb(k) : nullptr, H, emb(k + 1), ld_emb, H, 0, st));
   }
   // global sum pool
-  const float* pin = p.cat;
+  const float* pin = emb(L);
   int64_t ld_pin = Wc;
   if (c.pool) {
-    GCS_TIMED("pool_fwd", gcs_segment_sum_fwd(p.cat, Wc, bt.graph_ptr, bt.n_graphs, Wc, p.pooled, Wc, st));
+    GCS_TIMED("pool_fwd", gcs_segment_sum_fwd(emb(L), Wc, bt.graph_ptr, bt.n_graphs, Wc, p.pooled, Wc, st));
     pin = p.pooled;
   }
   // post-processing MLP
@@ -325,13 +336,16 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
                         const gcs_batch& bt, const float* dlogits, gcs_stream st) {
   const int H = p.H, Wc = p.Wc, L = p.L, P = p.P, Q = p.Q;
   const int64_t N = p.N, R = p.rows_post;
+  const bool cat = c.connectivity == 1;
+  auto emb = [&](int k) { return cat ? p.cat + static_cast<int64_t>(L - k) * H : p.cat + static_cast<int64_t>(k) * N * H; };
+  const int64_t ld_emb = cat ? Wc : H;
   // ---- post-processing MLP, last block first
   const float* da = dlogits;
   int64_t ldda = p.C;
   for (int j = Q - 1; j >= 0; --j) {
     const int bi = P + L + j;
     const BlockDesc& b = p.blocks[bi];
-    const float* in = j == 0 ? (c.pool ? p.pooled : p.cat) : p.post_a[j - 1];
+    const float* in = j == 0 ? (c.pool ? p.pooled : emb(L)) : p.post_a[j - 1];
     const int64_t ld_in = j == 0 ? Wc : H;
     float* din;
     int64_t lddin;
@@ -348,7 +362,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
   std::vector<const float*> Wp(L);
   std::vector<int> roff(L);
   cudaStream_t cst = as_stream(st);
-  for (int k = L - 1; k >= 0; --k) {
+  for (int k = L - 1; k >= 0 && cat; --k) {
     const int bi = P + k;
     const int nb = L - 1 - k;
     for (int q = 0; q < nb; ++q) {
@@ -391,7 +405,22 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
   }
   const float* da_pre;
   int64_t ldda_pre;
-  if (c.pool) {
+  if (!cat) {
+    // one running gradient g = dLoss/d(out_k): through z_k into the conv block, and - for 'sum' - straight on to out_{k-1}
+    float* g = p.gcat;
+    if (c.pool) {
+      GCS_TIMED("pool_bwd", gcs_segment_sum_bwd(p.dpooled, Wc, bt.graph_ptr, bt.n_graphs, H, p.tmp_c, H, st));
+      g = p.tmp_c;
+    }
+    for (int k = L - 1; k >= 0; --k) {
+      GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb4_blk_ptr_t, bt.rb4_ent_t, N, g, H, nullptr, nullptr,
+                                         nullptr, p.tmp_a, H, H, st));
+      GCS_TRY(block_backward(c, p, P + k, params, grads, p.tmp_a, H, p.h[P + k], H, N, emb(k), ld_emb, p.dhcat, H, g, H,
+                             c.connectivity == 2 ? 1 : 0, st));
+    }
+    da_pre = g;
+    ldda_pre = H;
+  } else if (c.pool) {
     GCS_TIMED("linear_bwd_input", dense_dx_concat(p.dhcat, ldd, Wp.data(), roff.data(), L, H, H, p.dpooled + static_cast<int64_t>(L) * H, Wc,
                                                   bt.seg_ids, bt.graph_ptr, bt.n_graphs, p.tmp_c, H, N, 0, p.lin_ws,
                                                   p.lin_ws_bytes, cst));

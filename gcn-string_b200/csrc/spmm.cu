@@ -78,7 +78,8 @@ template <bool kTransform>
 __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
     const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent, int n_rows, int n_blocks,
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, const float* __restrict__ shift,
-    const float* __restrict__ alpha, float* __restrict__ Y, int64_t ldy, int lanes, int slots, int iters) {
+    const float* __restrict__ alpha, const float* __restrict__ R, int64_t ldr, float* __restrict__ Y, int64_t ldy,
+    int lanes, int slots, int iters) {
   const int lane = threadIdx.x % lanes;
   const int slot = threadIdx.x / lanes;
   if (slot >= slots) return;
@@ -128,7 +129,13 @@ __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
 #pragma unroll
     for (int r = 0; r < kRB; ++r) {
       const int row = b * kRB + r;
-      if (row < n_rows) *reinterpret_cast<float4*>(Y + static_cast<int64_t>(row) * ldy + c) = acc[r];
+      if (row < n_rows) {
+        if (R) {                                     // Add()([z, out]): the skip operand joins after the aggregation
+          const float4 q = __ldg(reinterpret_cast<const float4*>(R + static_cast<int64_t>(row) * ldr + c));
+          acc[r].x += q.x; acc[r].y += q.y; acc[r].z += q.z; acc[r].w += q.w;
+        }
+        *reinterpret_cast<float4*>(Y + static_cast<int64_t>(row) * ldy + c) = acc[r];
+      }
     }
   }
 }
@@ -136,12 +143,17 @@ __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
 // Row-parallel CSR kernel.  VEC = 4: H % 4 == 0 and 16 B-aligned rows, lanes = H/4 threads per
 // row.  VEC = 1: any H, lanes = H threads per row.  A CTA walks a CONTIGUOUS chunk of rows:
 // consecutive rows of a banded matrix share most of their neighbours, which then hit in L1.
-template <int VEC, bool kTransform>
+// kGeneral adds what GeneralConv itself never asks for: per-entry weights `values` (CSR order),
+// aggregate = mean / max (scatter_mean = unsorted_segment_mean: sum / entry count, 0 for an empty row; scatter_max =
+// unsorted_segment_max: the lowest float for an empty row) and a residual R added after the aggregation.
+enum { kAggSum = 0, kAggMean = 1, kAggMax = 2 };
+template <int VEC, bool kTransform, bool kGeneral>
 __global__ void __launch_bounds__(256) spmm_rows_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int64_t n_rows,
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ alpha, float* __restrict__ Y,
-    int64_t ldy, int H, int lanes, int rows_per_block, int iters) {
+    int64_t ldy, int H, int lanes, int rows_per_block, int iters, const float* __restrict__ values,
+    const float* __restrict__ R, int64_t ldr, int agg) {
   const int lane = threadIdx.x % lanes;
   const int slot = threadIdx.x / lanes;
   const int c = lane * VEC;
@@ -170,8 +182,29 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(
     const int eb = __ldg(rowptr + r), ee = __ldg(rowptr + r + 1);
     float acc[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int k = 0; k < VEC; ++k) acc[k] = (kGeneral && agg == kAggMax) ? -3.402823466e+38f : 0.f;
     int e = eb;
+    if (kGeneral) {
+      for (; e < ee; ++e) {
+        float v[VEC];
+        load(__ldg(colidx + e), v);
+        const float w = values ? __ldg(values + e) : 1.f;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float m = values ? v[k] * w : v[k];
+          acc[k] = agg == kAggMax ? fmaxf(acc[k], m) : acc[k] + m;
+        }
+      }
+      if (agg == kAggMean && ee > eb) {
+        const float cnt = static_cast<float>(ee - eb);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = acc[k] / cnt;
+      }
+      if (R) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += __ldg(R + r * ldr + c + k);
+      }
+    }
     for (; e + 4 <= ee; e += 4) {
       const int j0 = __ldg(colidx + e), j1 = __ldg(colidx + e + 1);
       const int j2 = __ldg(colidx + e + 2), j3 = __ldg(colidx + e + 3);
@@ -206,6 +239,8 @@ struct SpmmArgs {
   const int32_t* rowptr; const int32_t* colidx; const int32_t* blk_ptr; const uint32_t* ent; int64_t n_rows;
   const float* X; int64_t ldx; const float* scale; const float* shift; const float* alpha;
   float* Y; int64_t ldy; int H; cudaStream_t st;
+  const float* values = nullptr; const float* R = nullptr; int64_t ldr = 0; int agg = 0;
+  bool general() const { return values || agg != kAggSum; }
 };
 
 int g_rows_iters = 16;   // tuning knob (gcs_debug_set_param 1)
@@ -218,10 +253,14 @@ int launch_rows(const SpmmArgs& a) {
   const int rows_per_block = 256 / lanes;
   const int iters = g_rows_iters;                   // rows_per_block * iters contiguous rows per CTA
   dim3 grid(static_cast<unsigned>(ceil_div(a.n_rows, static_cast<int64_t>(rows_per_block) * iters)));
-  if (a.scale)
-    spmm_rows_kernel<VEC, true><<<grid, 256, 0, a.st>>>(a.rowptr, a.colidx, a.n_rows, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, a.H, lanes, rows_per_block, iters);
-  else
-    spmm_rows_kernel<VEC, false><<<grid, 256, 0, a.st>>>(a.rowptr, a.colidx, a.n_rows, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, a.H, lanes, rows_per_block, iters);
+#define GCS_ROWS_LAUNCH(T, G)                                                                                          \
+  spmm_rows_kernel<VEC, T, G><<<grid, 256, 0, a.st>>>(a.rowptr, a.colidx, a.n_rows, a.X, a.ldx, a.scale, a.shift,      \
+                                                      a.alpha, a.Y, a.ldy, a.H, lanes, rows_per_block, iters, a.values, \
+                                                      a.R, a.ldr, a.agg)
+  const bool general = a.general() || a.R;
+  if (a.scale) { if (general) GCS_ROWS_LAUNCH(true, true); else GCS_ROWS_LAUNCH(true, false); }
+  else { if (general) GCS_ROWS_LAUNCH(false, true); else GCS_ROWS_LAUNCH(false, false); }
+#undef GCS_ROWS_LAUNCH
   GCS_CHECK_LAUNCH("spmm_rows_kernel");
   return GCS_OK;
 }
@@ -233,9 +272,9 @@ int launch_rb4(const SpmmArgs& a) {
   const int iters = g_rb4_iters;
   dim3 grid(static_cast<unsigned>(ceil_div(n_blocks, static_cast<int64_t>(slots) * iters)));
   if (a.scale)
-    spmm_rb4_kernel<true><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, lanes, slots, iters);
+    spmm_rb4_kernel<true><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.R, a.ldr, a.Y, a.ldy, lanes, slots, iters);
   else
-    spmm_rb4_kernel<false><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.Y, a.ldy, lanes, slots, iters);
+    spmm_rb4_kernel<false><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.R, a.ldr, a.Y, a.ldy, lanes, slots, iters);
   GCS_CHECK_LAUNCH("spmm_rb4_kernel");
   return GCS_OK;
 }
@@ -282,26 +321,41 @@ extern "C" int gcs_spmm_build_rb4(const int32_t* rowptr, const int32_t* colidx, 
   return GCS_OK;
 }
 
+extern "C" int gcs_spmm_aggregate(const int32_t* rowptr, const int32_t* colidx, const float* values,
+                                  const int32_t* rb4_blk_ptr, const uint32_t* rb4_ent, int64_t n_rows, const float* X,
+                                  int64_t ldx, const float* scale, const float* shift, const float* alpha,
+                                  const float* residual, int64_t ldr, float* Y, int64_t ldy, int32_t H,
+                                  int32_t aggregate, gcs_stream stream) {
+  GCS_CHECK_ARG(n_rows >= 0 && H > 0, "gcs_spmm_aggregate: bad size (n_rows=%lld, H=%d)", (long long)n_rows, H);
+  GCS_CHECK_ARG(aggregate == kAggSum || aggregate == kAggMean || aggregate == kAggMax,
+                "gcs_spmm_aggregate: aggregate must be 0 (sum), 1 (mean) or 2 (max)");
+  if (n_rows == 0) return GCS_OK;
+  GCS_CHECK_ARG(rowptr && colidx && X && Y, "gcs_spmm_aggregate: null pointer");
+  GCS_CHECK_ARG(ldx >= H && ldy >= H, "gcs_spmm_aggregate: leading dimension smaller than H");
+  GCS_CHECK_ARG(!residual || ldr >= H, "gcs_spmm_aggregate: residual leading dimension smaller than H");
+  GCS_CHECK_ARG((scale != nullptr) == (shift != nullptr) && (scale != nullptr) == (alpha != nullptr),
+                "gcs_spmm_aggregate: scale/shift/alpha must be all NULL or all set");
+  GCS_CHECK_ARG((rb4_blk_ptr != nullptr) == (rb4_ent != nullptr), "gcs_spmm_aggregate: rb4_blk_ptr and rb4_ent go together");
+  GCS_CHECK_ARG(X != Y, "gcs_spmm_aggregate: in-place aggregation is not defined");
+  GCS_CHECK_ARG(n_rows < INT32_MAX, "gcs_spmm_aggregate: n_rows exceeds int32 CSR range");
+  SpmmArgs a{rowptr, colidx, rb4_blk_ptr, rb4_ent, n_rows, X, ldx, scale, shift, alpha, Y, ldy, H, as_stream(stream)};
+  a.values = values; a.R = residual; a.ldr = ldr; a.agg = aggregate;
+  const bool vec_ok = (H % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
+                      (!scale || (aligned16(scale) && aligned16(shift) && aligned16(alpha)));
+  const bool res_ok = !residual || ((ldr % 4 == 0) && aligned16(residual));
+  // RB4 whenever the structure is supplied: with the BN+PReLU prologue one transform per block instead of per row
+  // (334 vs 463 us at cfg2), and for the plain gather of the backward 262 vs 319 us row by row.  The union entries
+  // carry no per-row weight, so weighted / mean / max aggregation runs row by row.
+  const bool want_rb4 = g_spmm_mode != 1 && !a.general();
+  if (want_rb4 && rb4_blk_ptr && vec_ok && res_ok && H / 4 <= 256 && 256 % (H / 4) == 0) return launch_rb4(a);
+  if (vec_ok) return launch_rows<4>(a);
+  return launch_rows<1>(a);
+}
+
 extern "C" int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb4_blk_ptr,
                             const uint32_t* rb4_ent, int64_t n_rows, const float* X, int64_t ldx,
                             const float* scale, const float* shift, const float* alpha, float* Y,
                             int64_t ldy, int32_t H, gcs_stream stream) {
-  GCS_CHECK_ARG(n_rows >= 0 && H > 0, "gcs_spmm_sum: bad size (n_rows=%lld, H=%d)", (long long)n_rows, H);
-  if (n_rows == 0) return GCS_OK;
-  GCS_CHECK_ARG(rowptr && colidx && X && Y, "gcs_spmm_sum: null pointer");
-  GCS_CHECK_ARG(ldx >= H && ldy >= H, "gcs_spmm_sum: leading dimension smaller than H");
-  GCS_CHECK_ARG((scale != nullptr) == (shift != nullptr) && (scale != nullptr) == (alpha != nullptr),
-                "gcs_spmm_sum: scale/shift/alpha must be all NULL or all set");
-  GCS_CHECK_ARG((rb4_blk_ptr != nullptr) == (rb4_ent != nullptr), "gcs_spmm_sum: rb4_blk_ptr and rb4_ent go together");
-  GCS_CHECK_ARG(X != Y, "gcs_spmm_sum: in-place aggregation is not defined");
-  GCS_CHECK_ARG(n_rows < INT32_MAX, "gcs_spmm_sum: n_rows exceeds int32 CSR range");
-  SpmmArgs a{rowptr, colidx, rb4_blk_ptr, rb4_ent, n_rows, X, ldx, scale, shift, alpha, Y, ldy, H, as_stream(stream)};
-  const bool vec_ok = (H % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
-                      (!scale || (aligned16(scale) && aligned16(shift) && aligned16(alpha)));
-  // RB4 whenever the structure is supplied: with the BN+PReLU prologue one transform per block instead of per row
-  // (334 vs 463 us at cfg2), and for the plain gather of the backward 262 vs 319 us row by row.
-  const bool want_rb4 = g_spmm_mode != 1;
-  if (want_rb4 && rb4_blk_ptr && vec_ok && H / 4 <= 256 && 256 % (H / 4) == 0) return launch_rb4(a);
-  if (vec_ok) return launch_rows<4>(a);
-  return launch_rows<1>(a);
+  return gcs_spmm_aggregate(rowptr, colidx, nullptr, rb4_blk_ptr, rb4_ent, n_rows, X, ldx, scale, shift, alpha, nullptr, 0,
+                            Y, ldy, H, kAggSum, stream);
 }

@@ -61,12 +61,13 @@ def _as_adjacency(a, n):
 class GeneralConv:
     def __init__(self, channels=256, batch_norm=True, dropout=0.0, aggregate="sum", activation="prelu",
                  use_bias=True, seed=0, **kwargs):
-        if aggregate != "sum":
-            raise NotImplementedError("native path implements aggregate='sum' only")
+        if aggregate not in ops.AGGREGATE:
+            raise NotImplementedError("native path implements aggregate in {'sum', 'mean', 'max'}")
         if dropout != 0.0:
             raise NotImplementedError("native path implements dropout=0.0 only")
         if activation not in ("prelu", None, "linear"):
             raise NotImplementedError("native path implements activation in {'prelu', None}")
+        self.aggregate = aggregate
         self.channels, self.use_batch_norm, self.activation, self.use_bias = channels, batch_norm, activation, use_bias
         self.seed = seed
         self.block = None
@@ -82,7 +83,9 @@ class GeneralConv:
         h = self.block.linear(x)
         scale, shift = self.block.fold(h, training)
         alpha = self.block.alpha if self.block.alpha is not None else torch.ones_like(scale)
-        return ops.spmm_sum(a.rowptr, a.colidx, h, scale, shift, alpha, rb4=a.rb4)
+        if self.aggregate == "sum":
+            return ops.spmm_sum(a.rowptr, a.colidx, h, scale, shift, alpha, rb4=a.rb4)
+        return ops.spmm_aggregate(a.rowptr, a.colidx, h, scale, shift, alpha, aggregate=self.aggregate)
 
 
 class GlobalSumPool:

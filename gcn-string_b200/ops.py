@@ -273,6 +273,41 @@ def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, rb
     return out
 
 
+AGGREGATE = {"sum": 0, "mean": 1, "max": 2}
+
+
+def spmm_aggregate(rowptr, colidx, x, scale=None, shift=None, alpha=None, values=None, residual=None,
+                   aggregate="sum", out=None, rb4=None):
+    """Y = agg_j(values_ij * prelu(x[j]*scale + shift, alpha)) + residual  (gcs_spmm_aggregate).
+    ``values``: float32 per stored entry in CSR order or None; ``aggregate`` in {'sum', 'mean', 'max'}
+    (Spektral's scatter_sum / scatter_mean / scatter_max); ``residual``: [n, H] or None."""
+    torch = _t()
+    lib = _lib.load()
+    if aggregate not in AGGREGATE:
+        raise ValueError(f"aggregate must be one of {sorted(AGGREGATE)}")
+    x, ldx = _mat(x, "x")
+    n, hdim = x.shape
+    if rowptr.shape[0] != n + 1:
+        raise ValueError(f"A has {rowptr.shape[0] - 1} rows but x has {n}")
+    if values is not None:
+        if values.shape[0] != colidx.shape[0]:
+            raise ValueError("values must hold one weight per stored entry")
+        values = values.to(device="cuda", dtype=torch.float32).contiguous()
+    ldr = 0
+    if residual is not None:
+        residual, ldr = _mat(residual, "residual")
+        if tuple(residual.shape) != (n, hdim):
+            raise ValueError("residual must have the shape of the output")
+    if out is None:
+        out = torch.empty(n, hdim, dtype=torch.float32, device="cuda")
+    out, ldy = _mat(out, "y")
+    bp, en = rb4 if rb4 is not None else (None, None)
+    check(lib.gcs_spmm_aggregate(ptr(rowptr), ptr(colidx), ptr(values), ptr(bp), ptr(en), n, ptr(x), ldx, ptr(scale),
+                                 ptr(shift), ptr(alpha), ptr(residual), ldr, ptr(out), ldy, hdim, AGGREGATE[aggregate],
+                                 stream_ptr()), "gcs_spmm_aggregate")
+    return out
+
+
 # ------------------------------------------------------------------ pooling (K4/K6)
 def segment_sum_fwd(x, graph_ptr, out=None):
     torch = _t()

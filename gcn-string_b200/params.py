@@ -51,8 +51,6 @@ class GNNConfig:
             raise NotImplementedError("native path implements pool in {'sum', None}")
         if self.connectivity not in CONNECTIVITY:
             raise ValueError("connectivity must be 'cat', 'sum' or None")
-        if self.connectivity == "sum":
-            raise NotImplementedError("connectivity='sum' is not built yet")
         if self.dropout != 0.0:
             raise NotImplementedError("native path implements dropout=0.0 only")
         if self.hidden_activation != "prelu":

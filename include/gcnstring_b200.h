@@ -170,6 +170,22 @@ int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb
                  const float* scale, const float* shift, const float* alpha, float* Y, int64_t ldy,
                  int32_t H, gcs_stream stream);
 
+/* General form (SURVEY.md 8 f3 and the 'sum' skip connection of GeneralGNN.call):
+ *   Y = agg_j( w_ij * f(X[j]) ) + residual
+ * values   : optional per-entry weights in CSR order (the reference computes `dca` / `proximity` edge attributes,
+ *            gcn.py:130-157, behind a `use_edge_data` switch); NULL = pattern only, as GeneralConv does.
+ * aggregate: 0 sum (scatter_sum), 1 mean (scatter_mean = unsorted_segment_mean: sum / number of entries of the row,
+ *            0 for an empty row), 2 max (scatter_max = unsorted_segment_max: the lowest float for an empty row).
+ * residual : optional [n_rows, H] operand added after the aggregation - Keras Add()([z, out]) of
+ *            connectivity='sum' - NULL otherwise.
+ * The RB4 kernel serves aggregate = 0 without weights (with or without residual); everything else runs row by row.
+ * gcs_spmm_sum(...) == gcs_spmm_aggregate(..., values = NULL, residual = NULL, aggregate = 0). */
+int gcs_spmm_aggregate(const int32_t* rowptr, const int32_t* colidx, const float* values,
+                       const int32_t* rb4_blk_ptr, const uint32_t* rb4_ent, int64_t n_rows, const float* X,
+                       int64_t ldx, const float* scale, const float* shift, const float* alpha,
+                       const float* residual, int64_t ldr, float* Y, int64_t ldy, int32_t H,
+                       int32_t aggregate, gcs_stream stream);
+
 /* ---------------------------------------------------------------------------------
  * K4/K6  GlobalSumPool = tf.math.segment_sum(X, i) over sorted graph ids, and its
  * gradient dX[n] = dOut[i[n]].

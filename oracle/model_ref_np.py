@@ -113,7 +113,8 @@ def forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=False):
         a, c = _block_fwd(blk, out, training, cfg.bn_epsilon)
         caches.append(c)
         z = spmm_sum(rows, cols, a, n)
-        out = np.concatenate([z, out], axis=1) if cfg.connectivity == "cat" else z
+        # Concatenate()([z, out]) | Add()([z, out]) | no skip connection (GeneralGNN.call)
+        out = np.concatenate([z, out], axis=1) if cfg.connectivity == "cat" else (z + out if cfg.connectivity == "sum" else z)
     node_out = out
     if cfg.pool == "sum":
         out = segment_sum(out, seg, n_graphs)
@@ -141,7 +142,7 @@ def accuracy(probs, y):
 def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs):
     """One training-mode forward + backward.  Returns dict(loss, acc, probs, grads (flat
     float64, same layout as w), new_state (flat float64 moving statistics))."""
-    assert cfg.activation == "softmax" and cfg.pool == "sum" and cfg.connectivity == "cat"
+    assert cfg.activation == "softmax" and cfg.pool == "sum" and cfg.connectivity in ("cat", "sum", None)
     y = y.astype(np.float64)
     probs, ctx = forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=True)
     blocks, caches, logits = ctx["blocks"], ctx["caches"], ctx["logits"]
@@ -155,7 +156,10 @@ def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs):
     dout = d[seg]                                       # grad of segment_sum
     for k in range(L - 1, -1, -1):
         bi = P + k
-        dz, dprev = dout[:, :H], dout[:, H:]
+        if cfg.connectivity == "cat":
+            dz, dprev = dout[:, :H], dout[:, H:]
+        else:                                           # Add: the gradient reaches both operands; None: only z
+            dz, dprev = dout, (dout if cfg.connectivity == "sum" else 0.0)
         da = spmm_sum(cols, rows, dz, x.shape[0])       # pattern(A)^T . dz
         dout = dprev + _block_bwd(blocks[bi], caches[bi], da, grads)
     for bi in range(P - 1, -1, -1):

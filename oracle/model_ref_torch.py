@@ -65,7 +65,7 @@ def forward(cfg, params, x, rows, cols, seg, n_graphs, training, stats=None):
         a = _block(p, out, training, cfg.bn_epsilon, stats)
         msgs = a[cols]                                      # tf.gather -> [nnz, H]
         z = torch.zeros(n, a.shape[1], dtype=a.dtype).index_add_(0, rows, msgs)
-        out = torch.cat([z, out], dim=1) if cfg.connectivity == "cat" else z
+        out = torch.cat([z, out], dim=1) if cfg.connectivity == "cat" else (z + out if cfg.connectivity == "sum" else z)
     if cfg.pool == "sum":
         out = torch.zeros(n_graphs, out.shape[1], dtype=out.dtype).index_add_(0, seg, out)
     for p in params[P + L:]:

@@ -341,6 +341,71 @@ def test_spmm_rb4_arbitrary_structure():
     assert rel_err(host(y_rows), _spmm_ref(a, host(x))) < TOL
 
 
+@pytest.mark.parametrize("H", [64, 6])
+@pytest.mark.parametrize("aggregate", ["sum", "mean", "max"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_spmm_aggregate_weights_mean_max_residual(H, aggregate, weighted):
+    """gcs_spmm_aggregate against a per-row NumPy restatement of Spektral's scatter_sum / scatter_mean / scatter_max
+    (tf.math.unsorted_segment_*: an empty row gives 0 for sum and mean, the lowest float for max), with per-entry
+    weights, the fused BatchNorm+PReLU prologue and a residual added after the aggregation."""
+    rng = np.random.default_rng(H + len(aggregate))
+    n = 400
+    a = random_csr(rng, n, 0.03).tolil()
+    a[17, :] = 0                                          # empty rows
+    a[200:204, :] = 0
+    a = sp.csr_matrix(a)
+    a.sort_indices()
+    x = rng.standard_normal((n, H)).astype(np.float32)
+    res = rng.standard_normal((n, H)).astype(np.float32)
+    vals = rng.uniform(-1, 2, a.nnz).astype(np.float32) if weighted else None
+    sc, sh, al = (rng.uniform(0.5, 1.5, H).astype(np.float32), rng.normal(0, 0.5, H).astype(np.float32),
+                  rng.uniform(0.1, 0.4, H).astype(np.float32))
+    z = x.astype(np.float64) * sc + sh
+    f = np.where(z > 0, z, al * z)
+    ref = np.zeros((n, H))
+    for r in range(n):
+        lo, hi = a.indptr[r], a.indptr[r + 1]
+        m = f[a.indices[lo:hi]] * (vals[lo:hi, None].astype(np.float64) if weighted else 1.0)
+        if aggregate == "max":
+            ref[r] = m.max(0) if hi > lo else np.finfo(np.float32).min
+        elif hi > lo:
+            ref[r] = m.sum(0) / ((hi - lo) if aggregate == "mean" else 1)
+    rp, ci = dev(a.indptr.astype(np.int32)), dev(a.indices.astype(np.int32))
+    y = ops.spmm_aggregate(rp, ci, dev(x), dev(sc), dev(sh), dev(al), values=None if vals is None else dev(vals),
+                           aggregate=aggregate)
+    assert rel_err(host(y), ref) < TOL
+    y = ops.spmm_aggregate(rp, ci, dev(x), dev(sc), dev(sh), dev(al), values=None if vals is None else dev(vals),
+                           residual=dev(res), aggregate=aggregate)
+    ref_r = np.where(ref == np.finfo(np.float32).min, ref, ref + res)
+    got = host(y)
+    keep = ref != np.finfo(np.float32).min               # lowest float + residual: not a meaningful number
+    assert rel_err(got[keep], ref_r[keep]) < TOL
+    with pytest.raises(ValueError):
+        ops.spmm_aggregate(rp, ci, dev(x), aggregate="median")
+
+
+def test_spmm_residual_on_the_row_block_kernel():
+    """Add()([z, out]): the RB4 kernel with a residual equals the row kernel with a residual bit for bit, and both equal
+    aggregate-then-add."""
+    lib = _lib.load()
+    ds = synthetic.make_dataset(5, seed=3, n_mean=300, deg=10, n_feat=4)
+    ids = np.arange(5, dtype=np.int64)
+    _, a, _, _ = g.data.DeviceGraphStore(ds).batch(dev(ids), ids)
+    rng = np.random.default_rng(0)
+    n, H = a.n_rows, 128
+    x, res = dev(rng.standard_normal((n, H)).astype(np.float32)), dev(rng.standard_normal((n, 2 * H)).astype(np.float32))
+    sc, sh, al = (dev(rng.uniform(0.5, 1.5, H).astype(np.float32)), dev(rng.normal(0, 0.5, H).astype(np.float32)),
+                  dev(rng.uniform(0.1, 0.4, H).astype(np.float32)))
+    plain = ops.spmm_sum(a.rowptr, a.colidx, x, sc, sh, al, rb4=a.rb4)
+    y_rb4 = ops.spmm_aggregate(a.rowptr, a.colidx, x, sc, sh, al, residual=res[:, H:], rb4=a.rb4)
+    try:
+        lib.gcs_debug_set_spmm_mode(1)
+        y_rows = ops.spmm_aggregate(a.rowptr, a.colidx, x, sc, sh, al, residual=res[:, H:], rb4=a.rb4)
+    finally:
+        lib.gcs_debug_set_spmm_mode(0)
+    assert torch.equal(y_rb4, y_rows) and torch.equal(y_rb4, plain + res[:, H:])
+
+
 def test_spmm_is_deterministic_and_handles_empty_rows():
     rng = np.random.default_rng(1)
     a = random_csr(rng, 500, 0.02)

@@ -34,7 +34,7 @@ class _Sparse:
 
 def make_model(cfg, w, s):
     kw = dict(hidden=cfg.hidden, message_passing=cfg.message_passing, pre_process=cfg.pre_process,
-              post_process=cfg.post_process, pool=cfg.pool)
+              post_process=cfg.post_process, pool=cfg.pool, connectivity=cfg.connectivity)
     m = g.GeneralGNN(cfg.output, activation=cfg.activation, **kw)
     m.build(cfg.in_features)
     m.load_flat(w, s)
@@ -192,11 +192,62 @@ def test_spektral_style_inputs_and_layers(small_case):
     act = h / np.sqrt(1 + 1e-3)                                        # fresh BN (moving stats 0/1), alpha = 0
     act = np.where(act > 0, act, 0.0)
     assert z.shape == (n, 16) and rel_err(host(z), O1.spmm_sum(rows, cols, act, n)) < TOL
+    # aggregate='mean' / 'max' (scatter_mean / scatter_max) at the layer level; every node has its self-loop
+    deg = np.bincount(rows, minlength=n)[:, None]
+    conv_mean = g.GeneralConv(channels=16, seed=3, aggregate="mean")
+    assert rel_err(host(conv_mean([xs, a])), O1.spmm_sum(rows, cols, act, n) / deg) < TOL
+    conv_max = g.GeneralConv(channels=16, seed=3, aggregate="max")
+    mx = np.full((n, 16), -np.inf)
+    np.maximum.at(mx, rows, act[cols])
+    assert rel_err(host(conv_max([xs, a])), mx) < TOL
+    with pytest.raises(NotImplementedError):
+        g.GeneralConv(channels=16, aggregate="prod")
 
 
 def test_node_level_output_without_pooling(small_case):
     c = small_case
     cfg = GNNConfig(in_features=12, output=3, activation=None, hidden=16, message_passing=2, pool=None)
+    w, s = g.init_params(cfg, seed=8, perturb=True)
+    model = make_model(cfg, w, s)
+    n = c["x"].shape[0]
+    out = model([torch.from_numpy(c["x"].astype(np.float32)).cuda(), _Sparse(c["idx"], n)])
+    ref, _ = O1.forward(cfg, block_specs(cfg), w, s, c["x"].astype(np.float32), c["idx"][:, 0], c["idx"][:, 1],
+                        c["seg"], 8, False)
+    assert out.shape == (n, 3) and rel_err(host(out), ref) < TOL
+
+
+@pytest.mark.parametrize("connectivity", ["sum", None])
+@pytest.mark.parametrize("hidden", [16, 128])
+def test_skip_connection_variants(small_case, connectivity, hidden):
+    """connectivity='sum' (Add()([z, out]), the skip operand joins in the aggregation's epilogue) and None: train step
+    (loss, probabilities, BatchNorm state, every gradient) and inference against the float64 oracle.  hidden = 128
+    sends the H x H transforms through the tensor-core kernels and the aggregation through the row-block kernel."""
+    c = small_case
+    cfg = GNNConfig(in_features=12, output=2, activation="softmax", hidden=hidden, message_passing=3, connectivity=connectivity)
+    specs = block_specs(cfg)
+    w, s = g.init_params(cfg, seed=12, perturb=True)
+    args = (cfg, specs, w, s, c["x"], c["idx"][:, 0], c["idx"][:, 1], c["seg"], c["y"], 8)
+    ref, o2 = O1.loss_and_grads(*args), O2.loss_and_grads(*args)
+    (x, a, i), y = next(g.DisjointLoader(c["ds"], batch_size=8, epochs=1, shuffle=False))
+    model = make_model(cfg, w, s)
+    loss_acc, probs = model.train_step_grads([x, a, i], y)
+    assert abs(host(loss_acc)[0] - ref["loss"]) < TOL * abs(ref["loss"])
+    assert rel_err(host(probs), ref["probs"]) < TOL
+    assert rel_err(host(model.state), ref["new_state"]) < TOL
+    assert_grads_close(host(model.grads), ref["grads"], cfg, o2["grads"])
+    g1 = model.grads.clone()
+    model.load_flat(w, s)
+    model.train_step_grads([x, a, i], y)
+    assert torch.equal(g1, model.grads)                       # deterministic
+    model.load_flat(w, s)
+    p_inf, _ = O1.forward(cfg, specs, w, s, c["x"], c["idx"][:, 0], c["idx"][:, 1], c["seg"], 8, False)
+    assert rel_err(host(model([x, a, i], training=False)), p_inf) < TOL
+
+
+@pytest.mark.parametrize("connectivity", ["sum", None])
+def test_skip_connection_variants_node_level(small_case, connectivity):
+    c = small_case
+    cfg = GNNConfig(in_features=12, output=3, activation=None, hidden=16, message_passing=2, pool=None, connectivity=connectivity)
     w, s = g.init_params(cfg, seed=8, perturb=True)
     model = make_model(cfg, w, s)
     n = c["x"].shape[0]
