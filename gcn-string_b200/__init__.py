@@ -4,7 +4,8 @@ Sub-modules: ``params`` (hyper-parameters + flat parameter layout), ``synthetic`
 (E. coli-shaped graph generator), ``_lib`` (ctypes binding of the C-ABI CUDA library),
 ``data`` / ``layers`` / ``models`` / ``optimizers`` / ``losses`` (the Spektral/Keras
 call surface the reference script uses), ``shards`` (packed device-ready ingest format),
-``evaluate`` (the reference's evaluation pass and ROC metrics), ``distributed`` (graph sharding + gradient
+``evaluate`` (the reference's evaluation pass and ROC metrics), ``contact`` (contact maps and pair graphs from CA
+coordinates on the device), ``distributed`` (graph sharding + gradient
 all-reduce).  Importing the package does not load CUDA; the first native call does and
 raises if ``libgcnstring_b200.so`` is missing — there is no CPU fallback.
 """
@@ -16,6 +17,7 @@ from .losses import CategoricalCrossentropy, categorical_accuracy  # noqa: F401,
 from .models import GeneralGNN, GradientTape  # noqa: F401,E402
 from . import optimizers  # noqa: F401,E402
 from . import shards  # noqa: F401,E402
+from . import contact  # noqa: F401,E402
 from .evaluate import auc, evaluate, roc_auc, roc_curve  # noqa: F401,E402
 
 __version__ = "0.1.0"

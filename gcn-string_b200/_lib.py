@@ -60,6 +60,11 @@ PROTOTYPES = {
     "gcs_spmm_rb4_workspace_bytes": (c_int64, [I64]),
     "gcs_spmm_build_rb4": (c_int32, [P, P, I64, I64, P, P, P, I64, P]),
     "gcs_spmm_sum": (c_int32, [P, P, P, P, I64, P, I64, P, P, P, P, I64, I32, P]),
+    "gcs_contact_workspace_bytes": (I64, [I64]),
+    "gcs_contact_map_rowptr": (c_int32, [P, P, I32, I64, ctypes.c_float, P, P, I64, P]),
+    "gcs_contact_map_fill": (c_int32, [P, P, I32, I64, ctypes.c_float, P, P, P, P]),
+    "gcs_link_pairs_offsets": (c_int32, [P, I32, P, P, I32, P, P, P, I64, P]),
+    "gcs_link_pairs": (c_int32, [P, P, P, P, P, I32, P, P, P, P, I64, P, P, P, P, I64, P]),
     "gcs_spmm_aggregate": (c_int32, [P, P, P, P, P, I64, P, I64, P, P, P, P, I64, P, I64, I32, I32, P]),
     "gcs_segment_sum_fwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_segment_sum_bwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),

@@ -198,13 +198,14 @@ __global__ void tr_count_kernel(const int32_t* __restrict__ colidx, int64_t nnz,
 // shuffle scan inside each warp, one shuffle scan of the 32 warp totals - two barriers per chunk
 // (a shared-memory Hillis-Steele scan with 20 barriers per 8 K chunk took 107 us for the 127 K row
 // blocks of a cfg2 batch).
+template <typename OutT>
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ cnt, int64_t n,
-                                                              int32_t* __restrict__ out) {
+                                                              OutT* __restrict__ out) {
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry_s;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   constexpr int PER = 16;
-  int32_t carry = 0;
+  OutT carry = 0;                                        // a chunk total fits int32, the running total may not
   for (int64_t base = 0; base < n; base += 1024 * PER) {
     int32_t v[PER];
     int32_t sum = 0;
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
       if (lane == 31) carry_s = winc;                    // chunk total
     }
     __syncthreads();
-    int32_t run = carry + warp_tot[warp] + inc - sum;
+    OutT run = carry + static_cast<OutT>(warp_tot[warp] + inc - sum);
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       if (b + k < n) out[b + k] = run;
@@ -282,8 +283,14 @@ __global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __res
 }
 
 // out[0..n] = exclusive prefix sums of cnt[0..n) (out[n] = total); shared with spmm.cu.
+int exclusive_scan_i64(const int32_t* cnt, int64_t n, int64_t* out, cudaStream_t st) {
+  exclusive_scan_kernel<int64_t><<<1, 1024, 0, st>>>(cnt, n, out);
+  GCS_CHECK_LAUNCH("exclusive_scan_kernel<int64>");
+  return GCS_OK;
+}
+
 int exclusive_scan_i32(const int32_t* cnt, int64_t n, int32_t* out, cudaStream_t st) {
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(cnt, n, out);
+  exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(cnt, n, out);
   GCS_CHECK_LAUNCH("exclusive_scan_kernel");
   return GCS_OK;
 }
@@ -374,7 +381,7 @@ extern "C" int gcs_csr_transpose(const int32_t* rowptr, const int32_t* colidx, i
     tr_count_kernel<<<static_cast<unsigned>(ceil_div(nnz, 256)), 256, 0, st>>>(colidx, nnz, workspace);
     GCS_CHECK_LAUNCH("tr_count_kernel");
   }
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(workspace, n_rows, rowptr_t);
+  exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(workspace, n_rows, rowptr_t);
   GCS_CHECK_LAUNCH("exclusive_scan_kernel");
   if (nnz > 0 && n_rows > 0) {
     GCS_CUDA(cudaMemsetAsync(workspace, 0, sizeof(int32_t) * (n_rows + 1), st));

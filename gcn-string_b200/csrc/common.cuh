@@ -19,6 +19,7 @@ inline cudaStream_t as_stream(gcs_stream s) { return reinterpret_cast<cudaStream
 int sm_count();
 
 int exclusive_scan_i32(const int32_t* cnt, int64_t n, int32_t* out, cudaStream_t st);   // batching.cu
+int exclusive_scan_i64(const int32_t* cnt, int64_t n, int64_t* out, cudaStream_t st);   // batching.cu (int64 running total)
 
 // Synchronised-BatchNorm hook (gcs_set_allreduce_hook), per host thread.
 struct SyncHook {

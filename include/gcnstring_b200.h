@@ -205,6 +205,40 @@ int gcs_softmax_xent(const float* logits, const float* y, int32_t B, int32_t C, 
                      float* loss_acc, float* dlogits, float grad_scale, gcs_stream stream);
 
 /* ---------------------------------------------------------------------------------
+ * K11  Residue contact maps of a batch of chains.  Replaces
+ * GraphMaker.calculate_residue_dist / calculate_dist_matrix / generate_proximity_matrix
+ * (src/utilities/gcn_utills.py:161-238): d = sqrt(sum((ca_i - ca_j)^2)) in float32 with NumPy's operation order
+ * and no fused multiply-add, adjacency = d < angstroms (the diagonal gives the self-loops), evaluated per chain.
+ *   ca[n_residues, 3] float32 (Bio.PDB atom coordinates), chain_ptr[n_chains + 1] int32 residue offsets.
+ *   gcs_contact_map_rowptr: rowptr[n_residues + 1] int64 (exclusive scan of the row counts; rowptr[n_residues] = nnz,
+ *     which the caller reads back to size `col`); workspace gcs_contact_workspace_bytes(n_residues).
+ *   gcs_contact_map_fill:   col[nnz] int32 chain-local column ids, ascending per row; dist[nnz] float32 (NULL-able),
+ *     the contact_map values the reference derives its `proximity` edge attribute from (:424-478).
+ * K12  Inter-protein pair graphs: GraphMaker.generate_graphs + link_graphs (:240-270, :319-377) followed by the
+ * adjacency gcn.py:104-117,184-197 takes from the union graph: nodes of chain pair_a[p] then of chain pair_b[p],
+ * both chains' contacts, plus one symmetric edge (bridge_a[q], n_a + bridge_b[q]) per DCA bridge
+ * q in [bridge_ptr[p], bridge_ptr[p+1]) (duplicates merged).  Output = the packed dataset layout K0 consumes:
+ *   gcs_link_pairs_offsets: node_off[n_pairs + 1] int64; *status_dev bit 0 = a chain id out of range.
+ *   gcs_link_pairs with col == NULL: rowptr[n_rows + 1] int64 (n_rows = node_off[n_pairs]); with col != NULL: fills
+ *     col[nnz] int32 pair-local ids, ascending per row.  *status_dev bit 1 = a bridge position outside its chain
+ *     (networkx would silently add a new node; here it is an error).
+ * --------------------------------------------------------------------------------- */
+int64_t gcs_contact_workspace_bytes(int64_t n_rows);
+int gcs_contact_map_rowptr(const float* ca, const int32_t* chain_ptr, int32_t n_chains, int64_t n_residues,
+                           float angstroms, int64_t* rowptr, void* workspace, int64_t workspace_bytes,
+                           gcs_stream stream);
+int gcs_contact_map_fill(const float* ca, const int32_t* chain_ptr, int32_t n_chains, int64_t n_residues,
+                         float angstroms, const int64_t* rowptr, int32_t* col, float* dist, gcs_stream stream);
+int gcs_link_pairs_offsets(const int32_t* chain_ptr, int32_t n_chains, const int32_t* pair_a, const int32_t* pair_b,
+                           int32_t n_pairs, int64_t* node_off, int32_t* status_dev, void* workspace,
+                           int64_t workspace_bytes, gcs_stream stream);
+int gcs_link_pairs(const int64_t* chain_rowptr, const int32_t* chain_col, const int32_t* chain_ptr,
+                   const int32_t* pair_a, const int32_t* pair_b, int32_t n_pairs, const int32_t* bridge_ptr,
+                   const int32_t* bridge_a, const int32_t* bridge_b, const int64_t* node_off, int64_t n_rows,
+                   int64_t* rowptr, int32_t* col, int32_t* status_dev, void* workspace, int64_t workspace_bytes,
+                   gcs_stream stream);
+
+/* ---------------------------------------------------------------------------------
  * K10  Fused multi-tensor optimizer steps over the flat parameter buffer.
  *   sgd:  w -= lr * (g * grad_scale)          (tf.keras.optimizers.SGD, gcn.py:325,338)
  *   adam: Keras Adam, lr_t = lr*sqrt(1-b2^t)/(1-b1^t), w -= lr_t*m/(sqrt(v)+eps)
