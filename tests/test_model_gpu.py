@@ -257,6 +257,47 @@ def test_skip_connection_variants_node_level(small_case, connectivity):
     assert out.shape == (n, 3) and rel_err(host(out), ref) < TOL
 
 
+@pytest.mark.parametrize("seed,F,H,host_store", [(0, 5, 12, False), (1, 3, 8, True), (2, 7, 20, False)])
+def test_irregular_graphs_directed_isolated_single_node(seed, F, H, host_store):
+    """Structures the synthetic generator never produces: DIRECTED adjacency (the backward then needs the transposed
+    pattern; indices[:, 0] is the target), nodes without any entry (empty rows - no self-loop), single-node
+    graphs, a graph without edges, explicit zeros and duplicates in the input matrix; feature / hidden widths that are
+    not multiples of 4.  Collate bit-exact against scipy, train step against the float64 oracle."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    graphs = []
+    for n in (1, 17, 2, 40, 1, 9, 23):
+        dense = (rng.random((n, n)) < 0.15).astype(np.int64)
+        dense[rng.integers(n)] = 0                                   # a node that receives nothing
+        a = sp.coo_matrix(dense)
+        a = sp.csr_matrix((np.concatenate([a.data, [0, 1, 1]]), (np.concatenate([a.row, [0, n - 1, n - 1]]),
+                                                                  np.concatenate([a.col, [0, 0, 0]]))), shape=(n, n))
+        y = np.eye(2, dtype=np.int64)[len(graphs) % 2]
+        graphs.append(g.Graph(x=rng.random((n, F)), a=a, y=y))
+    graphs[4].a = sp.csr_matrix((1, 1), dtype=np.int64)              # a single node without even a self-loop
+    (xr, (idx, _, _), seg), yr = batching_ref.collate([(gr.x, gr.a, gr.y) for gr in graphs])
+    B = len(graphs)
+    cfg = GNNConfig(in_features=F, output=2, activation="softmax", hidden=H, message_passing=3)
+    specs = block_specs(cfg)
+    w, s = g.init_params(cfg, seed=seed, perturb=True)
+    for b in specs:                                                   # no PReLU kink: strict tolerances apply
+        o, n = b.alpha
+        w[o:o + n] = 1.0
+    args = (cfg, specs, w, s, xr, idx[:, 0], idx[:, 1], seg, yr, B)
+    ref, o2 = O1.loss_and_grads(*args), O2.loss_and_grads(*args)
+    ds = synthetic.pack_graphs(graphs)
+    loader = g.DisjointLoader(ds, batch_size=B, epochs=1, shuffle=False, want_coo=True, device_resident=not host_store)
+    (x, a, i), y = next(loader)
+    assert np.array_equal(host(a.indices), idx) and np.array_equal(host(i), seg)
+    assert not a.symmetric
+    model = make_model(cfg, w, s)
+    loss_acc, probs = model.train_step_grads([x, a, i], y)
+    assert abs(host(loss_acc)[0] - ref["loss"]) < TOL * abs(ref["loss"])
+    assert rel_err(host(probs), ref["probs"]) < TOL
+    assert rel_err(host(model.state), ref["new_state"]) < TOL
+    assert_grads_close(host(model.grads), ref["grads"], cfg, o2["grads"])
+
+
 def test_gradient_tape_training_loop_matches_oracle(small_case):
     """The reference's train_step (gcn.py:328-340) written against this package, three SGD
     steps with the reference's PiecewiseConstantDecay, against the oracle's weights."""
