@@ -105,6 +105,10 @@ extern "C" int gcs_version(void) { return 100; }   // 0.1.0
 extern "C" const char* gcs_last_error(void) { return gcs::error_buffer(); }
 
 namespace gcs {
+AmaxSink& amax_sink() {
+  static thread_local AmaxSink s;
+  return s;
+}
 SyncHook& sync_hook() {
   static thread_local SyncHook h;
   return h;

@@ -185,9 +185,10 @@ template <int VEC>
 __global__ void __launch_bounds__(256) bn_prelu_fwd_kernel(
     const float* __restrict__ h, int64_t ldh, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ alpha, float* __restrict__ out,
-    int64_t ldo, int64_t M, int C) {
+    int64_t ldo, int64_t M, int C, float* __restrict__ amax) {
   const int cpr = (C + VEC - 1) / VEC;   // column groups per row
   const int64_t total = M * cpr;
+  float mx = 0.f;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = idx / cpr;
@@ -205,11 +206,15 @@ __global__ void __launch_bounds__(256) bn_prelu_fwd_kernel(
         v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
       }
       *reinterpret_cast<float4*>(out + r * ldo + c) = v;
+      mx = amax4(mx, v);
     } else {
       const float z = fmaf(__ldg(h + r * ldh + c), __ldg(scale + c), __ldg(shift + c));
-      out[r * ldo + c] = alpha ? (z > 0.f ? z : __ldg(alpha + c) * z) : z;
+      const float o = alpha ? (z > 0.f ? z : __ldg(alpha + c) * z) : z;
+      out[r * ldo + c] = o;
+      mx = fmaxf(mx, fabsf(o));
     }
   }
+  amax_commit(mx, amax);
 }
 
 // Backward pass 1: per column S1 = sum dz, S2 = sum dz*xhat, S3 = sum da*min(z,0), with
@@ -377,10 +382,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const float* __restrict__ da, int64_t ldda, const float* __restrict__ h, int64_t ldh,
     const float* __restrict__ mean, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ alpha, const float* __restrict__ coef, float* __restrict__ dh, int64_t lddh,
-    int64_t M, int C, int64_t rows_per_split, double* __restrict__ colsum_ws) {
+    int64_t M, int C, int64_t rows_per_split, double* __restrict__ colsum_ws, float* __restrict__ amax) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + lane) * VEC;
   const bool valid = c < C;
+  float mx = 0.f;
   const int64_t rb = blockIdx.y * rows_per_split;
   int64_t re = rb + rows_per_split;
   if (re > M) re = M;
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o[u][k] = out(hv[u][k], gv[u][k], k);
+        for (int k = 0; k < VEC; ++k) { o[u][k] = out(hv[u][k], gv[u][k], k); mx = fmaxf(mx, fabsf(o[u][k])); }
         if (VEC == 4) *reinterpret_cast<float4*>(dh + (r + 8 * u) * lddh + c) = make_float4(o[u][0], o[u][1], o[u][2], o[u][3]);
         else dh[(r + 8 * u) * lddh + c] = o[u][0];
       }
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
         gv[0] = __ldg(da + r * ldda + c);
       }
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o[k] = out(hv[k], gv[k], k);
+      for (int k = 0; k < VEC; ++k) { o[k] = out(hv[k], gv[k], k); mx = fmaxf(mx, fabsf(o[k])); }
       if (VEC == 4) *reinterpret_cast<float4*>(dh + r * lddh + c) = make_float4(o[0], o[1], o[2], o[3]);
       else dh[r * lddh + c] = o[0];
       if (colsum_ws) {
@@ -457,6 +463,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
       }
     }
   }
+  amax_commit(mx, amax);
   if (colsum_ws) block_store_partials<VEC>(csum, colsum_ws + static_cast<int64_t>(blockIdx.y) * C + c, 0, 0, valid);
 }
 
@@ -537,8 +544,8 @@ extern "C" int gcs_bn_prelu_fwd(const float* h, int64_t ldh, const float* scale,
   const bool vec = (C % 4 == 0) && (ldh % 4 == 0) && (ldo % 4 == 0) && aligned16(h) && aligned16(out) &&
                    aligned16(scale) && aligned16(shift) && (!alpha || aligned16(alpha));
   cudaStream_t st = as_stream(stream);
-  if (vec) bn_prelu_fwd_kernel<4><<<static_cast<unsigned>(elementwise_blocks(M * (C / 4))), 256, 0, st>>>(h, ldh, scale, shift, alpha, out, ldo, M, C);
-  else bn_prelu_fwd_kernel<1><<<static_cast<unsigned>(elementwise_blocks(M * C)), 256, 0, st>>>(h, ldh, scale, shift, alpha, out, ldo, M, C);
+  if (vec) bn_prelu_fwd_kernel<4><<<static_cast<unsigned>(elementwise_blocks(M * (C / 4))), 256, 0, st>>>(h, ldh, scale, shift, alpha, out, ldo, M, C, amax_sink().produce);
+  else bn_prelu_fwd_kernel<1><<<static_cast<unsigned>(elementwise_blocks(M * C)), 256, 0, st>>>(h, ldh, scale, shift, alpha, out, ldo, M, C, amax_sink().produce);
   GCS_CHECK_LAUNCH("bn_prelu_fwd_kernel");
   return GCS_OK;
 }
@@ -579,8 +586,8 @@ extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, i
     GCS_CHECK_LAUNCH("bn_bwd_final_kernel");
   }
   double* cws = dbias ? ws : nullptr;          // the reduction partials are consumed: reuse their space
-  if (vec) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);
-  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws);
+  if (vec) bn_bwd_apply_kernel<4><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws, amax_sink().produce);
+  else bn_bwd_apply_kernel<1><<<grid, kBnThreads, 0, st>>>(da, ldda, h, ldh, mean, gamma, beta, alpha, coef, dh, lddh, M, C, g.rows_per_split, cws, amax_sink().produce);
   GCS_CHECK_LAUNCH("bn_bwd_apply_kernel");
   if (dbias) {
     bn_bwd_dbias_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, dbias);

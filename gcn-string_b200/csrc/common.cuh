@@ -29,6 +29,29 @@ struct SyncHook {
 };
 SyncHook& sync_hook();
 
+// Running |max| of the tensors the fp16 tensor-core GEMM reads (linear_tc.cu): while `produce` is set, the kernels
+// that write activations / gradients (bn_prelu_fwd, the aggregation, the BatchNorm backward apply pass) fold the |max|
+// of what they write into *produce (atomicMax on the bit pattern; the caller zeroes the cell); while `consume` is set,
+// the dense transforms take it as the |max| of their A operand.  Per host thread, set by model.cu around its calls.
+struct AmaxSink {
+  float* produce = nullptr;
+  const float* consume = nullptr;
+};
+AmaxSink& amax_sink();
+
+// Fold a thread's |max| (m >= 0) into *cell (no-op for cell == nullptr): one REDUX over the lanes that are here, then
+// one atomic by the first of them, and only if it would raise the cell.  Safe under divergence.
+__device__ __forceinline__ void amax_commit(float m, float* cell) {
+  if (!cell) return;
+  const unsigned mask = __activemask();
+  const unsigned bits = __reduce_max_sync(mask, __float_as_uint(m));      // non-negative floats order like their bits
+  if ((threadIdx.x & 31) == static_cast<unsigned>(__ffs(mask) - 1) && bits > *reinterpret_cast<volatile unsigned*>(cell))
+    atomicMax(reinterpret_cast<unsigned*>(cell), bits);
+}
+__device__ __forceinline__ float amax4(float m, const float4& v) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+
 // Count of kernel launches issued by this library (bench.py's `gpu_launches`).
 void count_launch();
 

@@ -264,6 +264,16 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
 int split(const float* W, int rows, int cols, bool transpose, float* hi, float* lo, cudaStream_t st);
 int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, float* hi, float* lo,
                   cudaStream_t st);
+int f16_mode();
+bool f16_shape_ok(int K);
+float* f16_cells(void* workspace, int K, int N);
+int f16_begin(float* cells, cudaStream_t st);
+int absmax(const float* A, int64_t lda, int64_t M, int K, float* cell, cudaStream_t st);
+int split_f16_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, void* hi, void* lo,
+                      float* cells, cudaStream_t st);
+int launch_f16(const float* A, int64_t lda, const void* Bt_hi, const void* Bt_lo, const float* cells, const float* a_amax,
+               const float* bias, float* C, int64_t ldc, int64_t M, int K, int N, int accumulate, cudaStream_t st,
+               const float* rowbias = nullptr, int64_t ld_rowbias = 0, const int64_t* seg = nullptr);
 bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* dH, int64_t ldh);
 void wgrad_split(int64_t M, int K, int N, int* splits, int* kb_per_split);
 int64_t wgrad_workspace_bytes(int64_t M, int K, int N);
@@ -287,6 +297,24 @@ static int try_tensor_cores(const float* A, int64_t lda, const float* W, int w_r
                   workspace_bytes >= tc::split_workspace_bytes(Kred, Nout);
   if (!ok) {
     if (g_gemm_mode == 2) return fail(GCS_ERR_UNSUPPORTED, "tensor-core GEMM forced but shape/workspace do not allow it");
+    return GCS_OK;
+  }
+  // fp16 split (half the tensor time) when the |max| of A is known: from the producer kernels of the fused model
+  // (amax_sink().consume), or - debug mode 2 - from an extra pass over A.
+  const float* a_amax = amax_sink().consume;
+  if (tc::f16_mode() && tc::f16_shape_ok(Kred) && (a_amax || tc::f16_mode() == 2)) {
+    char* hi = static_cast<char*>(workspace);
+    char* lo = hi + 2LL * Kred * Nout;
+    float* cells = tc::f16_cells(workspace, Kred, Nout);
+    GCS_TRY(tc::f16_begin(cells, st));
+    GCS_TRY(tc::absmax(W, w_cols, w_rows, w_cols, cells, st));
+    if (!a_amax) {
+      GCS_TRY(tc::absmax(A, lda, M, Kred, cells + 2, st));
+      a_amax = cells + 2;
+    }
+    GCS_TRY(tc::split_f16_strided(W, w_rows, w_cols, w_cols, transpose_w, transpose_w ? w_rows : w_cols, hi, lo, cells, st));
+    GCS_TRY(tc::launch_f16(A, lda, hi, lo, cells, a_amax, bias, C, ldc, M, Kred, Nout, accumulate, st));
+    *used = 1;
     return GCS_OK;
   }
   float* hi = static_cast<float*>(workspace);
@@ -327,6 +355,23 @@ int dense_dx_concat(const float* dh, int64_t ld, const float* const* W, const in
   const bool tc_ok = g_gemm_mode != 1 && n_blocks > 0 && tc::shape_ok(M, Kred, Nout, dh, ld, C, ldc, nullptr) && workspace &&
                      aligned16(workspace) && workspace_bytes >= tc::split_workspace_bytes(Kred, Nout) &&
                      (!rowbias || (ld_rowbias % 4 == 0 && aligned16(rowbias)));
+  const float* a_amax = amax_sink().consume;
+  if (tc_ok && tc::f16_mode() && tc::f16_shape_ok(Kred) && (a_amax || tc::f16_mode() == 2)) {
+    char* hi = static_cast<char*>(workspace);
+    char* lo = hi + 2LL * Kred * Nout;
+    float* cells = tc::f16_cells(workspace, Kred, Nout);
+    GCS_TRY(tc::f16_begin(cells, st));
+    for (int b = 0; b < n_blocks; ++b)
+      GCS_TRY(tc::absmax(W[b] + static_cast<int64_t>(row_off[b]) * Hred, Hred, Nout, Hred, cells, st));
+    if (!a_amax) {
+      GCS_TRY(tc::absmax(dh, ld, M, Kred, cells + 2, st));
+      a_amax = cells + 2;
+    }
+    for (int b = 0; b < n_blocks; ++b)   // Bt[c][b*Hred + n] = W_b[row_off_b + c][n]
+      GCS_TRY(tc::split_f16_strided(W[b] + static_cast<int64_t>(row_off[b]) * Hred, Nout, Hred, Hred, false, Kred,
+                                    hi + 2LL * b * Hred, lo + 2LL * b * Hred, cells, st));
+    return tc::launch_f16(dh, ld, hi, lo, cells, a_amax, nullptr, C, ldc, M, Kred, Nout, accumulate, st, rowbias, ld_rowbias, seg);
+  }
   if (tc_ok) {
     float* hi = static_cast<float*>(workspace);
     float* lo = hi + static_cast<int64_t>(Kred) * Nout;

@@ -21,6 +21,7 @@
 //   wgrad_tc_kernel         weight gradient: reduction over the rows, A^T gathered into tensor memory,
 //                           dH split in shared memory as an MN-major operand
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -110,6 +111,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -158,12 +170,27 @@ constexpr uint32_t P_B_BYTES = 64 * BK * 4;              // 8 KB per weight half
 constexpr uint32_t P_STAGE_BYTES = A_RAW_BYTES + 2 * P_B_BYTES;   // 32 KB
 constexpr uint32_t P_OUT_BYTES = 32 * 32 * 4;            // per converter warp: one 32 x 32 output box staged for the TMA store
 constexpr uint32_t kPSmemBytes = kPStages * P_STAGE_BYTES + kConvWarps * P_OUT_BYTES + 1024 + 256;
+// fp16 variant (see linear_tc_pair_kernel<true>): K blocks of 64 - two raw fp32 A boxes (32 KB) and the two weight
+// halves as fp16 [64 x 64] (8 KB each, 128 B rows like the tf32 tiles) - four stages.
+// Converting 64 K elements per row costs ~3x the instructions of the tf32 split of 32 while the tensor time per K block
+// stays the same, so the fp16 variant runs SIXTEEN converter warps (four per tensor-memory lane quarter, 16 K elements
+// each; 576 threads, <= 112 registers: the epilogue reads its 32 x 32 box in two halves) and three 48 KB stages.
+constexpr int kHStages = 3;
+constexpr int BKH = 64;
+constexpr int kHConvWarps = 16;
+constexpr int kHThreads = 64 + 32 * kHConvWarps;
+constexpr uint32_t H_STAGE_BYTES = 2 * A_RAW_BYTES + 2 * P_B_BYTES;   // 48 KB
+constexpr uint32_t kHSmemBytes = kHStages * H_STAGE_BYTES + kHConvWarps * P_OUT_BYTES + 1024 + 256;
+static_assert(kHSmemBytes <= 232448, "fp16 pair kernel exceeds the 227 KB of shared memory per CTA");
 constexpr uint32_t P_ACC1 = 0, P_ACC2 = 256, P_A_COL = 384;
 // M = 256 across the pair; N = 256 / 128
 constexpr uint32_t kPairDesc256 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
                                   (static_cast<uint32_t>(256 >> 4) << 24);
 constexpr uint32_t kPairDesc128 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(128 >> 3) << 17) |
                                   (static_cast<uint32_t>(256 >> 4) << 24);
+// the same shapes for kind::f16 with F16 operands (format 0) and an F32 accumulator
+constexpr uint32_t kPairDesc256H = (1u << 4) | (static_cast<uint32_t>(256 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+constexpr uint32_t kPairDesc128H = (1u << 4) | (static_cast<uint32_t>(128 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
 
 __device__ __forceinline__ void mma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -171,6 +198,32 @@ __device__ __forceinline__ void mma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tme
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// fp16 operand split of two neighbouring K elements (already multiplied by the operand's power-of-two scale):
+// hi = fp16(y), lo = fp16((y - hi) * 2^11) - both parts carry 11 significant bits in fp16's range, the pair 22 bits
+// like the tf32 split; element 2i sits in the low half of the 32-bit tensor-memory cell.
+__device__ __forceinline__ void split_f16x2(float y0, float y1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(y0, y1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((y0 - hf.x) * 2048.f, (y1 - hf.y) * 2048.f);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// Power-of-two scale that brings an operand with the given |max| to [2^13, 2^14) (fp16 overflows at 65504); 1 for an
+// all-zero or non-finite maximum.
+__device__ __forceinline__ float f16_scale(float amax) {
+  const uint32_t e = (__float_as_uint(amax) >> 23) & 0xFFu;
+  if (e == 0u || e == 0xFFu) return 1.f;
+  int se = 127 + 13 - (static_cast<int>(e) - 127);
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  return __uint_as_float(static_cast<uint32_t>(se) << 23);
 }
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -208,14 +261,27 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_tc_pair_kernel(
+// kF16 = true: the same pipeline on kind::f16 MMAs (K = 16 per instruction at the K = 8 tf32 rate, i.e. half the tensor
+// time per product).  Operands are split into fp16 hi + 2^11-scaled fp16 lo (22 bits, as the tf32 split); fp16's narrow
+// exponent range is handled by a power-of-two scale per operand: A is multiplied by f16_scale(*a_amax) in the converters
+// (a_amax = running |max| of the tensor, maintained by its producer kernels), the weights by b_scale in the split
+// kernel; the epilogue undoes both.  Elements more than 2^28 below the operand's maximum lose relative precision -
+// an absolute error of 2^-36 of the maximum, far below fp32 rounding of the sums they enter.
+template <bool kF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : kThreads, 1) linear_tc_pair_kernel(
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
     const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_c,
     const float* __restrict__ bias, int64_t M, int K, int n_tiles, int num_tiles, int accumulate,
-    const float* __restrict__ rowbias, int64_t ld_rowbias, const int64_t* __restrict__ seg) {
+    const float* __restrict__ rowbias, int64_t ld_rowbias, const int64_t* __restrict__ seg,
+    const float* __restrict__ a_amax, const float* __restrict__ b_scale_inv) {
+  constexpr int kPStages = kF16 ? kHStages : tc::kPStages;
+  constexpr uint32_t P_STAGE_BYTES = kF16 ? H_STAGE_BYTES : tc::P_STAGE_BYTES;
+  constexpr uint32_t A_BYTES = kF16 ? 2 * A_RAW_BYTES : A_RAW_BYTES;
+  constexpr int BK = kF16 ? BKH : tc::BK;
+  constexpr int kConvWarps = kF16 ? kHConvWarps : tc::kConvWarps;
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t out_stage = base + kPStages * P_STAGE_BYTES;       // 1024 B aligned (stages are 32 KB)
+  const uint32_t out_stage = base + kPStages * P_STAGE_BYTES;       // 1024 B aligned (stages are 32 / 48 KB)
   const uint32_t bars = out_stage + kConvWarps * P_OUT_BYTES;
   // barriers (8 B each): full[6] | smem_empty[6] | a_ready[2] | a_empty[2] | acc_full | tmem ptr
   auto full = [&](int s) { return bars + 8u * s; };
@@ -274,8 +340,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
           const uint32_t a_raw = base + s * P_STAGE_BYTES;
           mbar_arrive_expect_tx(full(s), P_STAGE_BYTES);
           tma_load_2d(a_raw, &map_a, kb * BK, m0, full(s));
-          tma_load_2d(a_raw + A_RAW_BYTES, &map_b_hi, kb * BK, n0 + 64 * rank, full(s));
-          tma_load_2d(a_raw + A_RAW_BYTES + P_B_BYTES, &map_b_lo, kb * BK, n0 + 64 * rank, full(s));
+          if (kF16) tma_load_2d(a_raw + A_RAW_BYTES, &map_a, kb * BK + 32, m0, full(s));
+          tma_load_2d(a_raw + A_BYTES, &map_b_hi, kb * BK, n0 + 64 * rank, full(s));
+          tma_load_2d(a_raw + A_BYTES + P_B_BYTES, &map_b_lo, kb * BK, n0 + 64 * rank, full(s));
         }
       }
     }
@@ -296,14 +363,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
           mbar_wait(a_ready(t), (it / kPAStages) & 1);
           tc_fence_after();
           if (leader) {
-            const uint64_t d_b = make_kmajor_sw128_desc(base + s * P_STAGE_BYTES + A_RAW_BYTES);
+            const uint64_t d_b = make_kmajor_sw128_desc(base + s * P_STAGE_BYTES + A_BYTES);
             const uint32_t a_hi = tmem_base + P_A_COL + t * 64;
+            // four instructions per operand either way: K = 8 tf32 or K = 16 fp16 elements = 32 B of a weight row
+            // and 8 tensor-memory columns of A per step
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
               const uint64_t koff = static_cast<uint64_t>((k * 32) >> 4);
               const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              mma_tf32_ts_pair(tmem_base + P_ACC1, a_hi + k * 8, d_b + koff, kPairDesc256, acc);        // A_hi . [B_hi ; B_lo]
-              mma_tf32_ts_pair(tmem_base + P_ACC2, a_hi + 32 + k * 8, d_b + koff, kPairDesc128, acc);   // A_lo . B_hi
+              if (kF16) {
+                mma_f16_ts_pair(tmem_base + P_ACC1, a_hi + k * 8, d_b + koff, kPairDesc256H, acc);
+                mma_f16_ts_pair(tmem_base + P_ACC2, a_hi + 32 + k * 8, d_b + koff, kPairDesc128H, acc);
+              } else {
+                mma_tf32_ts_pair(tmem_base + P_ACC1, a_hi + k * 8, d_b + koff, kPairDesc256, acc);        // A_hi . [B_hi ; B_lo]
+                mma_tf32_ts_pair(tmem_base + P_ACC2, a_hi + 32 + k * 8, d_b + koff, kPairDesc128, acc);   // A_lo . B_hi
+              }
             }
             tc_commit_pair(smem_empty(s));
             tc_commit_pair(a_empty(t));
@@ -320,30 +394,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t it = 0, tile_iter = 0;
+    float a_scale = 1.f, out_scale = 1.f;
+    if (kF16) {
+      a_scale = f16_scale(__ldg(a_amax));
+      out_scale = (1.f / a_scale) * __ldg(b_scale_inv);       // powers of two: exact
+    }
     for (int tile = blockIdx.y; tile < num_tiles; tile += gridDim.y, ++tile_iter) {
       const int n0 = (tile % n_tiles) * BN;
       const int64_t m0 = (static_cast<int64_t>(tile / n_tiles) * 2 + rank) * BM;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % kPStages, t = it % kPAStages;
         mbar_wait(full(s), (it / kPStages) & 1);
-        const uint32_t row_addr = base + s * P_STAGE_BYTES + r * 128;
         uint32_t hi[16], lo[16];
+        if (kF16) {
+          // `half` = 0..3 here: 16 of the 64 K elements = four 16 B chunks of raw box half >> 1 -> 8 + 8 packed pairs
+          const uint32_t row_addr = base + s * P_STAGE_BYTES + (half >> 1) * A_RAW_BYTES + r * 128;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float4 v;
-          const uint32_t addr = row_addr + (((4 * half + c) ^ (r & 7)) << 4);          // undo the 128 B TMA swizzle
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-          const float e[4] = {v.x, v.y, v.z, v.w};
+          for (int c = 0; c < 4; ++c) {
+            float4 v;
+            const uint32_t addr = row_addr + (((4 * (half & 1) + c) ^ (r & 7)) << 4);    // undo the 128 B TMA swizzle
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            split_f16x2(v.x * a_scale, v.y * a_scale, hi[2 * c], lo[2 * c]);
+            split_f16x2(v.z * a_scale, v.w * a_scale, hi[2 * c + 1], lo[2 * c + 1]);
+          }
+        } else {
+          const uint32_t row_addr = base + s * P_STAGE_BYTES + r * 128;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) split_tf32(e[i], hi[4 * c + i], lo[4 * c + i]);
+          for (int c = 0; c < 4; ++c) {
+            float4 v;
+            const uint32_t addr = row_addr + (((4 * half + c) ^ (r & 7)) << 4);          // undo the 128 B TMA swizzle
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(e[i], hi[4 * c + i], lo[4 * c + i]);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_empty(s));
         mbar_wait(a_empty(t), ((it / kPAStages) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_hi = tmem_base + lane_addr + P_A_COL + t * 64 + 16 * half;
-        tmem_st16(a_hi, hi);
-        tmem_st16(a_hi + 32, lo);
+        if (kF16) {
+          const uint32_t a_hi = tmem_base + lane_addr + P_A_COL + t * 64 + 8 * half;
+          const uint32_t (&h8)[8] = *reinterpret_cast<const uint32_t(*)[8]>(hi);
+          const uint32_t (&l8)[8] = *reinterpret_cast<const uint32_t(*)[8]>(lo);
+          tmem_st8(a_hi, h8);
+          tmem_st8(a_hi + 32, l8);
+        } else {
+          const uint32_t a_hi = tmem_base + lane_addr + P_A_COL + t * 64 + 16 * half;
+          tmem_st16(a_hi, hi);
+          tmem_st16(a_hi + 32, lo);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -359,32 +459,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
       // 128-bit shared stores per thread and one bulk copy that drains while the warp is already converting the
       // next tile.  Rows past M are clipped by the tensor map.
       const uint32_t sbuf = out_stage + (warp - 2) * P_OUT_BYTES;
-#pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-        uint32_t v[32], w[32], u[32];
-        const uint32_t mcol = c0 < 64 ? c0 : 64 + c0;        // [0,64) -> [0,64), [64,128) -> [128,192)
-        tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol, v);
-        tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol + 64, w);
-        tmem_ld32(tmem_base + lane_addr + P_ACC2 + c0, u);
+      if (kF16) {
+        // one 32 x 32 box per warp (columns [32 * half, +32)), read from tensor memory in two halves of 16 columns
+        const int c0 = half * 32;
+        const uint32_t mcol = c0 < 64 ? c0 : 64 + c0;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has left this buffer
         __syncwarp();
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[16], w[16], u[16];
+          tmem_ld16(tmem_base + lane_addr + P_ACC1 + mcol + 16 * hh, v);
+          tmem_ld16(tmem_base + lane_addr + P_ACC1 + mcol + 64 + 16 * hh, w);
+          tmem_ld16(tmem_base + lane_addr + P_ACC2 + c0 + 16 * hh, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = make_float4(__uint_as_float(v[4 * q]) + (__uint_as_float(w[4 * q]) + __uint_as_float(u[4 * q])),
-                                 __uint_as_float(v[4 * q + 1]) + (__uint_as_float(w[4 * q + 1]) + __uint_as_float(u[4 * q + 1])),
-                                 __uint_as_float(v[4 * q + 2]) + (__uint_as_float(w[4 * q + 2]) + __uint_as_float(u[4 * q + 2])),
-                                 __uint_as_float(v[4 * q + 3]) + (__uint_as_float(w[4 * q + 3]) + __uint_as_float(u[4 * q + 3])));
-          if (bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          for (int q = 0; q < 4; ++q) {
+            // the correction accumulators carry the 2^11 of the low parts; then undo the operand scales
+            float4 o = make_float4(fmaf(__uint_as_float(w[4 * q]) + __uint_as_float(u[4 * q]), 1.f / 2048.f, __uint_as_float(v[4 * q])) * out_scale,
+                                   fmaf(__uint_as_float(w[4 * q + 1]) + __uint_as_float(u[4 * q + 1]), 1.f / 2048.f, __uint_as_float(v[4 * q + 1])) * out_scale,
+                                   fmaf(__uint_as_float(w[4 * q + 2]) + __uint_as_float(u[4 * q + 2]), 1.f / 2048.f, __uint_as_float(v[4 * q + 2])) * out_scale,
+                                   fmaf(__uint_as_float(w[4 * q + 3]) + __uint_as_float(u[4 * q + 3]), 1.f / 2048.f, __uint_as_float(v[4 * q + 3])) * out_scale);
+            const int qq = 4 * hh + q;
+            if (bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + qq);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (rb) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + qq);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            const uint32_t dst = sbuf + lane * 128 + ((qq ^ (lane & 7)) << 4);          // SWIZZLE_128B box layout
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
           }
-          if (rb) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + q);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          const uint32_t dst = sbuf + lane * 128 + ((q ^ (lane & 7)) << 4);          // SWIZZLE_128B box layout
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -395,6 +501,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_
             else tma_store_2d(&map_c, sbuf, n0 + c0, crow);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+  #pragma unroll 1
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+          uint32_t v[32], w[32], u[32];
+          const uint32_t mcol = c0 < 64 ? c0 : 64 + c0;        // [0,64) -> [0,64), [64,128) -> [128,192)
+          tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol, v);
+          tmem_ld32(tmem_base + lane_addr + P_ACC1 + mcol + 64, w);
+          tmem_ld32(tmem_base + lane_addr + P_ACC2 + c0, u);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has left this buffer
+          __syncwarp();
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  #pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(__uint_as_float(v[4 * q]) + (__uint_as_float(w[4 * q]) + __uint_as_float(u[4 * q])),
+                                   __uint_as_float(v[4 * q + 1]) + (__uint_as_float(w[4 * q + 1]) + __uint_as_float(u[4 * q + 1])),
+                                   __uint_as_float(v[4 * q + 2]) + (__uint_as_float(w[4 * q + 2]) + __uint_as_float(u[4 * q + 2])),
+                                   __uint_as_float(v[4 * q + 3]) + (__uint_as_float(w[4 * q + 3]) + __uint_as_float(u[4 * q + 3])));
+            if (bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (rb) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + q);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            const uint32_t dst = sbuf + lane * 128 + ((q ^ (lane & 7)) << 4);          // SWIZZLE_128B box layout
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const int crow = static_cast<int>(m0) + quarter * 32;
+            if (crow < M) {
+              if (accumulate) tma_reduce_add_2d(&map_c, sbuf, n0 + c0, crow);
+              else tma_store_2d(&map_c, sbuf, n0 + c0, crow);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
       }
       tc_fence_before();          // accumulator reads ordered before this warp's next a_ready arrive
@@ -426,6 +571,36 @@ __global__ void __launch_bounds__(256) split_weights_kernel(const float* __restr
     const int64_t o = transpose ? c * ldo + r : r * ldo + c;
     hi[o] = h;
     lo[o] = l;
+  }
+}
+
+// |max| of a strided matrix into *cell (pre-zeroed; non-negative floats order like their bit patterns).
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int K, float* cell) {
+  float m = 0.f;
+  for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
+    const float* row = A + r * lda;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(row + c)));
+  }
+  amax_commit(m, cell);
+}
+
+// fp16 split of the weights for linear_tc_pair_kernel<true>: hi = fp16(w * s), lo = fp16((w * s - hi) * 2^11) with
+// s = f16_scale(*amax); *scale_inv = 1 / s for the epilogue.
+__global__ void __launch_bounds__(256) split_weights_f16_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
+                                                                int transpose, int64_t ldo, __half* __restrict__ hi,
+                                                                __half* __restrict__ lo, const float* __restrict__ amax,
+                                                                float* __restrict__ scale_inv) {
+  const float s = f16_scale(__ldg(amax));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *scale_inv = 1.f / s;
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<int64_t>(r) * cols);
+    const float y = __ldg(W + r * ldw + c) * s;
+    const __half h = __float2half_rn(y);
+    const int64_t o = transpose ? c * ldo + r : r * ldo + c;
+    hi[o] = h;
+    lo[o] = __float2half_rn((y - __half2float(h)) * 2048.f);
   }
 }
 
@@ -907,6 +1082,21 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t in
   return GCS_OK;
 }
 
+// 2-D fp16 tensor [rows, inner], row pitch ld elements; box = [box_rows, 64] = 128 B rows, SWIZZLE_128B.
+static int make_map_f16(CUtensorMap* map, const __half* ptr, int64_t rows, int64_t inner, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(__half)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BKH), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", static_cast<int>(r));
+  return GCS_OK;
+}
+
 bool shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* C, int64_t ldc, const float* bias) {
   return M > 0 && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && ldc % 4 == 0 && aligned16(A) && aligned16(C) &&
          (!bias || aligned16(bias)) && ceil_div(M, 2 * BM) * (N / BN) < (1LL << 30);
@@ -917,6 +1107,8 @@ int split_strided(const float* W, int rows, int cols, int64_t ldw, bool transpos
 
 int64_t split_workspace_bytes(int K, int N) { return round_up(2LL * K * N * sizeof(float), 256); }
 
+static int g_max_chain_k_f16 = 1024;                     // ... of the fp16 variant (K = 16 per step: 64 steps; 96 left one hidden-512 gradient tensor 1.3e-5 off)
+void set_max_chain_k_f16(int k) { if (k >= BKH && k % BKH == 0) g_max_chain_k_f16 = k; }
 static int g_max_chain_k = 768;                          // longest tensor-core accumulation chain of the forward / dX kernel
 void set_max_chain_k(int k) { if (k >= BK && k % BK == 0) g_max_chain_k = k; }
 
@@ -928,7 +1120,7 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
   GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));        // output boxes of 32 rows x 32 columns (128 B rows, SWIZZLE_128B)
   static bool attr = false;
   if (!attr) {
-    GCS_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
+    GCS_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     attr = true;
   }
   const int n_tiles = N / BN;
@@ -947,10 +1139,78 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
     GCS_TRY(make_map(&mh, Bt_hi + k0, N, kc, K, 64));
     GCS_TRY(make_map(&ml, Bt_lo + k0, N, kc, K, 64));
     const bool first = k0 == 0;
-    linear_tc_pair_kernel<<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
-                                                               first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
-                                                               seg);
+    linear_tc_pair_kernel<false><<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
+                                                                      first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
+                                                                      seg, nullptr, nullptr);
     GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
+  }
+  return GCS_OK;
+}
+
+// ---- fp16 variant -------------------------------------------------------------------------------------------------
+// Workspace of one GEMM: [hi fp16 N*K | lo fp16 N*K | cells: weights amax, 1/weights scale, scratch A amax] - inside
+// split_workspace_bytes(K, N) (the tf32 split needs twice the operand bytes).
+static int g_f16 = 1;      // 0 = tf32 kernels only, 1 = fp16 where the caller knows the A operand's |max|, 2 = fp16 everywhere (|max| by an extra pass)
+void set_f16_mode(int v) { if (v >= 0 && v <= 2) g_f16 = v; }
+int f16_mode() { return g_f16; }
+bool f16_shape_ok(int K) { return K % BKH == 0; }
+float* f16_cells(void* workspace, int K, int N) {
+  return reinterpret_cast<float*>(static_cast<char*>(workspace) + round_up(4LL * K * N, 256));
+}
+int64_t f16_workspace_bytes(int K, int N) { return round_up(4LL * K * N, 256) + 256; }
+
+int f16_begin(float* cells, cudaStream_t st) {
+  GCS_CUDA(cudaMemsetAsync(cells, 0, 3 * sizeof(float), st));
+  return GCS_OK;
+}
+int absmax(const float* A, int64_t lda, int64_t M, int K, float* cell, cudaStream_t st) {
+  int64_t blocks = M < 8LL * sm_count() ? M : 8LL * sm_count();
+  if (blocks < 1) blocks = 1;
+  absmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(A, lda, M, K, cell);
+  GCS_CHECK_LAUNCH("absmax_kernel");
+  return GCS_OK;
+}
+int split_f16_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, void* hi, void* lo,
+                      float* cells, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+  split_weights_f16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(W, rows, cols, ldw, transpose ? 1 : 0, ldo,
+                                                                        static_cast<__half*>(hi), static_cast<__half*>(lo),
+                                                                        cells, cells + 1);
+  GCS_CHECK_LAUNCH("split_weights_f16_kernel");
+  return GCS_OK;
+}
+
+// Bt: fp16 split weights [N][K] (hi, lo), cells as left by split_f16_strided; a_amax: device |max| of A.
+int launch_f16(const float* A, int64_t lda, const void* Bt_hi, const void* Bt_lo, const float* cells, const float* a_amax,
+               const float* bias, float* C, int64_t ldc, int64_t M, int K, int N, int accumulate, cudaStream_t st,
+               const float* rowbias, int64_t ld_rowbias, const int64_t* seg) {
+  alignas(64) CUtensorMap ma, mh, ml, mc;
+  GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));
+  static bool attr = false;
+  if (!attr) {
+    GCS_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBytes));
+    attr = true;
+  }
+  const int n_tiles = N / BN;
+  const int num_tiles = static_cast<int>(ceil_div(M, 2 * BM)) * n_tiles;
+  const int pairs = num_tiles < sm_count() / 2 ? num_tiles : sm_count() / 2;
+  dim3 grid(2, pairs);
+  const __half* bh = static_cast<const __half*>(Bt_hi);
+  const __half* bl = static_cast<const __half*>(Bt_lo);
+  // chains as in launch(): a K = 16 step adds into the accumulator with the same truncation, half as many steps per K
+  const int kMaxChainK = g_max_chain_k_f16;
+  for (int k0 = 0; k0 < K; k0 += kMaxChainK) {
+    const int kc = K - k0 < kMaxChainK ? K - k0 : kMaxChainK;
+    GCS_TRY(make_map(&ma, A + k0, M, kc, lda, BM));
+    GCS_TRY(make_map_f16(&mh, bh + k0, N, kc, K, 64));
+    GCS_TRY(make_map_f16(&ml, bl + k0, N, kc, K, 64));
+    const bool first = k0 == 0;
+    linear_tc_pair_kernel<true><<<grid, kHThreads, kHSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
+                                                                     first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
+                                                                     seg, a_amax, cells + 1);
+    GCS_CHECK_LAUNCH("linear_tc_pair_kernel<f16>");
   }
   return GCS_OK;
 }

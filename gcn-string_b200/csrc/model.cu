@@ -134,6 +134,17 @@ struct Plan {
   float* dpooled = nullptr;     // [B, Wc]
   void* lw_ws = nullptr;
   int64_t lw_ws_bytes = 0;
+  float* amax = nullptr;        // [0] running |max| of the node-level activations, [1] of the pre-BatchNorm gradients dh
+};
+
+// Sets the thread's AmaxSink for the calls inside a scope (see common.cuh: feeds the fp16 tensor-core GEMMs).
+struct AmaxScope {
+  AmaxSink saved;
+  AmaxScope(float* produce, const float* consume) : saved(amax_sink()) {
+    amax_sink().produce = produce;
+    amax_sink().consume = consume;
+  }
+  ~AmaxScope() { amax_sink() = saved; }
 };
 
 static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training, void* ws, Plan& p, int64_t* total) {
@@ -143,6 +154,7 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
   p.N = N; p.B = B;
   p.rows_post = c.pool ? B : N;
   Arena a(ws);
+  p.amax = a.take<float>(64);
   const int64_t NH = N * p.H;
   p.cat = a.take<float>(NH * (p.L + 1));         // 'cat': one [N, H(L+1)] matrix; otherwise L+1 slabs [N, H]
   p.h.assign(p.P + p.L, nullptr);
@@ -252,11 +264,16 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
   // out_k, the node embedding after k conv layers: the trailing (k+1)H columns of `cat`, or slab k
   auto emb = [&](int k) { return cat ? p.cat + static_cast<int64_t>(L - k) * H : p.cat + static_cast<int64_t>(k) * N * H; };
   const int64_t ld_emb = cat ? Wc : H;
+  // Every node-level activation written from here on folds its |max| into amax[0]; the dense transforms that read
+  // them (all but the one on the raw features) take it as the |max| of their A operand (fp16 split, linear_tc.cu).
+  GCS_CUDA(cudaMemsetAsync(p.amax, 0, sizeof(float), as_stream(st)));
+  AmaxScope node_scope(p.amax, nullptr);
   // pre-processing MLP
   const float* in = bt.x;
   int64_t ld_in = bt.ldx;
   for (int j = 0; j < P; ++j) {
     const BlockDesc& b = p.blocks[j];
+    amax_sink().consume = j > 0 ? p.amax : nullptr;
     GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
     float* out = j < P - 1 ? p.act[j] : emb(0);
@@ -267,6 +284,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     ld_in = ld_out;
   }
   // message passing with in-place concat
+  amax_sink().consume = p.amax;
   for (int k = 0; k < L; ++k) {
     const int bi = P + k;
     const BlockDesc& b = p.blocks[bi];
@@ -280,6 +298,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
                                              c.connectivity == 2 ? emb(k) : nullptr, H, emb(k + 1), ld_emb, H, 0, st));
   }
   // global sum pool
+  amax_sink() = AmaxSink();                                 // pooled rows and the post-MLP: tf32 kernels / CUDA cores
   const float* pin = emb(L);
   int64_t ld_pin = Wc;
   if (c.pool) {
@@ -316,11 +335,14 @@ static int block_backward(const gcs_model_config& c, const Plan& p, int bi, cons
   const BlockDesc& b = p.blocks[bi];
   const float* mean = p.stat[bi];
   const float* var = mean + b.m_out;
+  float* const dh_amax = const_cast<float*>(amax_sink().consume);      // set for the node-level blocks only
+  amax_sink().produce = dh_amax;
   GCS_TIMED("bn_prelu_bwd", gcs_bn_prelu_bwd(da, ldda, h, ldh, mean, var, params + b.gamma(), params + b.beta(),
                                              b.has_alpha ? params + b.alpha() : nullptr, c.bn_epsilon, dh, lddh,
                                              grads + b.gamma(), grads + b.beta(),
                                              b.has_alpha ? grads + b.alpha() : nullptr, grads + b.bias(), rows, b.m_out,
                                              p.bn_ws, p.bn_ws_bytes, st));
+  amax_sink().produce = nullptr;
   // the bias gradient (column sums of dh) came out of the BatchNorm backward's apply pass
   GCS_TIMED("linear_bwd_weight", gcs_linear_bwd_weight(in, ld_in, dh, lddh, grads + b.kernel(), nullptr, rows,
                                                        b.k_in, b.m_out, p.lw_ws, p.lw_ws_bytes, st));
@@ -339,6 +361,9 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
   const bool cat = c.connectivity == 1;
   auto emb = [&](int k) { return cat ? p.cat + static_cast<int64_t>(L - k) * H : p.cat + static_cast<int64_t>(k) * N * H; };
   const int64_t ld_emb = cat ? Wc : H;
+  // dh of every node-level block folds its |max| into amax[1] (BatchNorm backward apply pass); the input-gradient
+  // GEMMs read dh as their A operand
+  GCS_CUDA(cudaMemsetAsync(p.amax + 1, 0, sizeof(float), as_stream(st)));
   // ---- post-processing MLP, last block first
   const float* da = dlogits;
   int64_t ldda = p.C;
@@ -356,6 +381,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
     da = din;
     ldda = lddin;
   }
+  AmaxScope node_scope(nullptr, p.amax + 1);
   // ---- message passing, last layer first.  Block z_k of cat (columns [(L-1-k)H, (L-k)H)) is read by
   // the pool and by every later conv layer k' > k (rows [(k'-1-k)H, (k'-k)H) of its kernel).
   const int64_t ldd = static_cast<int64_t>(L) * H;

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
     const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent, int n_rows, int n_blocks,
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ alpha, const float* __restrict__ R, int64_t ldr, float* __restrict__ Y, int64_t ldy,
-    int lanes, int slots, int iters) {
+    int lanes, int slots, int iters, float* __restrict__ amax) {
   const int lane = threadIdx.x % lanes;
   const int slot = threadIdx.x / lanes;
   if (slot >= slots) return;
@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
     return v;
   };
   const int b_begin = blockIdx.x * slots * iters;
+  float mx = 0.f;
   for (int it = 0; it < iters; ++it) {
     const int b = b_begin + it * slots + slot;
     if (b >= n_blocks) break;
@@ -135,9 +136,11 @@ __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
           acc[r].x += q.x; acc[r].y += q.y; acc[r].z += q.z; acc[r].w += q.w;
         }
         *reinterpret_cast<float4*>(Y + static_cast<int64_t>(row) * ldy + c) = acc[r];
+        if (amax) mx = amax4(mx, acc[r]);
       }
     }
   }
+  amax_commit(mx, amax);
 }
 
 // Row-parallel CSR kernel.  VEC = 4: H % 4 == 0 and 16 B-aligned rows, lanes = H/4 threads per
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ alpha, float* __restrict__ Y,
     int64_t ldy, int H, int lanes, int rows_per_block, int iters, const float* __restrict__ values,
-    const float* __restrict__ R, int64_t ldr, int agg) {
+    const float* __restrict__ R, int64_t ldr, int agg, float* __restrict__ amax) {
   const int lane = threadIdx.x % lanes;
   const int slot = threadIdx.x / lanes;
   const int c = lane * VEC;
@@ -178,6 +181,7 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(
       for (int k = 0; k < VEC; ++k) v[k] = bn_prelu(v[k], sc[k], sh[k], al[k]);
     }
   };
+  float mx = 0.f;
   auto do_row = [&](int64_t r) {
     const int eb = __ldg(rowptr + r), ee = __ldg(rowptr + r + 1);
     float acc[VEC];
@@ -222,11 +226,14 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(
     float* q = Y + r * ldy + c;
     if (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     else q[0] = acc[0];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) mx = fmaxf(mx, fabsf(acc[k]));
   };
   const int64_t chunk = static_cast<int64_t>(rows_per_block) * iters;
   const int64_t rbeg = static_cast<int64_t>(blockIdx.x) * chunk;
   const int64_t rend = rbeg + chunk < n_rows ? rbeg + chunk : n_rows;
   for (int64_t r = rbeg + slot; r < rend; r += rows_per_block) do_row(r);
+  amax_commit(mx, amax);
 }
 
 }  // namespace gcs
@@ -256,7 +263,7 @@ int launch_rows(const SpmmArgs& a) {
 #define GCS_ROWS_LAUNCH(T, G)                                                                                          \
   spmm_rows_kernel<VEC, T, G><<<grid, 256, 0, a.st>>>(a.rowptr, a.colidx, a.n_rows, a.X, a.ldx, a.scale, a.shift,      \
                                                       a.alpha, a.Y, a.ldy, a.H, lanes, rows_per_block, iters, a.values, \
-                                                      a.R, a.ldr, a.agg)
+                                                      a.R, a.ldr, a.agg, amax_sink().produce)
   const bool general = a.general() || a.R;
   if (a.scale) { if (general) GCS_ROWS_LAUNCH(true, true); else GCS_ROWS_LAUNCH(true, false); }
   else { if (general) GCS_ROWS_LAUNCH(false, true); else GCS_ROWS_LAUNCH(false, false); }
@@ -272,9 +279,9 @@ int launch_rb4(const SpmmArgs& a) {
   const int iters = g_rb4_iters;
   dim3 grid(static_cast<unsigned>(ceil_div(n_blocks, static_cast<int64_t>(slots) * iters)));
   if (a.scale)
-    spmm_rb4_kernel<true><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.R, a.ldr, a.Y, a.ldy, lanes, slots, iters);
+    spmm_rb4_kernel<true><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.R, a.ldr, a.Y, a.ldy, lanes, slots, iters, amax_sink().produce);
   else
-    spmm_rb4_kernel<false><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.R, a.ldr, a.Y, a.ldy, lanes, slots, iters);
+    spmm_rb4_kernel<false><<<grid, 256, 0, a.st>>>(a.blk_ptr, a.ent, static_cast<int>(a.n_rows), n_blocks, a.X, a.ldx, a.scale, a.shift, a.alpha, a.R, a.ldr, a.Y, a.ldy, lanes, slots, iters, amax_sink().produce);
   GCS_CHECK_LAUNCH("spmm_rb4_kernel");
   return GCS_OK;
 }
@@ -285,13 +292,15 @@ int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 whenever supplie
 
 // Test / sweep hook (not part of the drop-in surface).
 extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
-namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); void set_wgrad_pair(int v); } }
+namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); void set_wgrad_pair(int v); void set_f16_mode(int v); void set_max_chain_k_f16(int k); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
   if (id == 2 && value > 0) g_rb4_iters = value;
   if (id == 3) gcs::tc::set_wgrad_chain(value);
   if (id == 5) gcs::tc::set_max_chain_k(value);
   if (id == 4) gcs::tc::set_wgrad_pair(value);
+  if (id == 7) gcs::tc::set_f16_mode(value);             // 0 tf32 only, 1 fp16 inside the fused model, 2 fp16 everywhere
+  if (id == 8) gcs::tc::set_max_chain_k_f16(value);
 }
 
 extern "C" int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows) {
