@@ -264,27 +264,40 @@ def run_b200(args):
         flops = 2.0 * n_nodes * (N_FEAT * HIDDEN + HIDDEN * HIDDEN + HIDDEN * HIDDEN * sum(range(1, LAYERS + 1)))
         t = ms / steps_prof / 1e3
         ach = flops / t / 1e12
-        tf32_peak = tensor_peak / 2.0
-        roofline_tensor = {"kernel": "linear_tc_pair_kernel (K1, forward dense transforms; 3 TF32 tcgen05 MMAs per fp32 product)",
-                           "bound": "tensor", "achieved": ach, "achieved_executed_tf32": 3.0 * ach, "peak": tf32_peak,
-                           "unit": "TFLOP/s", "frac": 3.0 * ach / tf32_peak,
-                           "peak_source": peak_src + " (MEASURED_PEAKS.json bf16_tflops_sustained / 2: TF32 runs at half the bf16 "
+        roofline_tensor = {"kernel": "linear_tc_pair_kernel<f16> (K1, forward dense transforms; 3 fp16 tcgen05 MMAs per fp32 "
+                                     "product: hi*hi + hi*lo + lo*hi of fp16-split operands)",
+                           "bound": "tensor", "achieved": ach, "achieved_executed_f16": 3.0 * ach, "peak": tensor_peak,
+                           "unit": "TFLOP/s", "frac": 3.0 * ach / tensor_peak,
+                           "peak_source": peak_src + " (MEASURED_PEAKS.json bf16_tflops_sustained: kind::f16 runs at the bf16 "
                                           "rate; sustained figure, the GEMMs run back to back under the power cap)",
                            "flops_per_step_fwd": flops, "ms_per_step_fwd_gemms": t * 1e3,
-                           "note": "frac counts the three TF32 passes as executed work; the first layer (K=32) and the "
-                                   "pooled post-MLP run on the FFMA path and are included in the time"}
+                           "note": "frac counts the three fp16 passes as executed work; the kernel is bound by the L2->SM "
+                                   "ingest of the raw fp32 activations (32 of 48 KB per 64-wide K block), not by the tensor "
+                                   "pipe; the first layer (K=32, tf32 split) and the pooled post-MLP are included in the time"}
     del loader, model, trainer
     torch.cuda.empty_cache()
 
     # ------------------------------------------------ host-resident arm (`e2e`)
     loader_h, model_h, trainer_h = make(False, False)
-    io = {}
+    io = {"k": 0}
+    host_loss = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
 
     def step_e2e():
+        # every step: the batch's graphs are copied out of pinned host memory (H2D, cudaMemcpyAsync of the slices), the
+        # batching kernel and the train step run, {loss, acc} go back to a pinned host buffer (D2H); the host READS the
+        # result of step t-1 while step t runs, so that the read does not drain the GPU queue (the copies of all K
+        # steps are inside the timed region)
+        k = io["k"]
         (x, a, i), y = next(loader_h)
         loss_acc, _ = trainer_h.train_step((x, a, i), y)
-        io["loss"] = loss_acc.cpu()                                  # D2H read of the step's result
+        host_loss[k % 2].copy_(loss_acc, non_blocking=True)
+        copied[k % 2].record()
+        if k > 0:
+            copied[(k - 1) % 2].synchronize()
+            io["loss"] = float(host_loss[(k - 1) % 2][0])
         io["h2d"] = loader_h.store.h2d_bytes_last
+        io["k"] = k + 1
     for _ in range(W):
         step_e2e()
     ms_e2e = timed(step_e2e, K)
@@ -314,8 +327,9 @@ def run_b200(args):
                          "every step", "bn": ("synchronised BatchNorm statistics (16 extra fp64 all-reduces of <= 3H+1 values per step)"
                           if args.sync_bn and world > 1 else "replica-local BatchNorm statistics")},
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(io["h2d"]),
-                "d2h_bytes_per_step": 8, "note": "dataset in pinned host memory; per step: H2D of the batch's packed "
-                "graphs, device batching, train step, D2H of {loss, acc}"},
+                "d2h_bytes_per_step": 8, "note": "dataset in pinned host memory, consecutive batches; per step: H2D of the batch's "
+                "packed graphs (cudaMemcpyAsync from the pinned arrays), device batching, train step, D2H of {loss, acc} into a "
+                "pinned buffer that the host reads one step later"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -386,6 +386,31 @@ def test_loader_epochs_shuffle_and_short_last_batch():
     assert parts[0][0].shape[0] == 3 and parts[1][0].shape[0] == 2
 
 
+def test_host_store_zero_copy_and_staged_upload_equal_the_resident_store():
+    """device_resident=False: the batching kernel reading the pinned host dataset directly (zero_copy=True) and the
+    staged route (host gather -> pinned buffer -> cudaMemcpyAsync) both yield bit-identical batches to the HBM-resident
+    store, shuffled and with a short last batch; the byte counts they report are those of the batch's graphs."""
+    ds = synthetic.make_dataset(11, seed=5, n_mean=50, deg=8, n_feat=7)
+    runs = []
+    for kw in (dict(device_resident=True), dict(device_resident=False, zero_copy=True), dict(device_resident=False)):
+        np.random.seed(77)
+        ld = g.DisjointLoader(ds, batch_size=4, epochs=2, shuffle=True, want_coo=True, prefetch=False, **kw)
+        out = []
+        for (x, a, i), y in ld:
+            out.append([host(t) for t in (x, a.indices, a.rowptr, a.colidx, a.graph_ptr, i, y)])
+            if not kw["device_resident"]:
+                b, n, nnz = y.shape[0], x.shape[0], a.nnz
+                assert 4 * nnz + 4 * 7 * n <= ld.store.h2d_bytes_last <= 4 * nnz + 4 * 7 * n + 16 * n + 64 * b + 64
+        runs.append(out)
+    assert len(runs[0]) == 6
+    np.random.seed(77)                                        # and with the next batch in flight on a side stream
+    ld = g.DisjointLoader(ds, batch_size=4, epochs=2, shuffle=True, want_coo=True, device_resident=False, zero_copy=True, prefetch=True)
+    runs.append([[host(t) for t in (x, a.indices, a.rowptr, a.colidx, a.graph_ptr, i, y)] for (x, a, i), y in ld])
+    for other in runs[1:]:
+        for b0, b1 in zip(runs[0], other):
+            assert all(np.array_equal(u, v) for u, v in zip(b0, b1))
+
+
 def test_loader_over_shards_equals_loader_over_graphs(tmp_path):
     """§8 f1: a dataset converted to packed shards (shards.write_dataset) and memory-mapped back
     drives the loader to bit-identical batches, from HBM and from pinned host memory."""
