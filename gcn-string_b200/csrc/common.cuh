@@ -35,7 +35,9 @@ SyncHook& sync_hook();
 // the dense transforms take it as the |max| of their A operand.  Per host thread, set by model.cu around its calls.
 struct AmaxSink {
   float* produce = nullptr;
-  const float* consume = nullptr;
+  const float* consume = nullptr;       // |max| of the A operand of gcs_linear_fwd / gcs_linear_bwd_input / dense_dx_concat,
+                                        // and of dH in gcs_linear_bwd_weight
+  const float* consume_act = nullptr;   // |max| of the activations A in gcs_linear_bwd_weight
 };
 AmaxSink& amax_sink();
 

@@ -278,7 +278,8 @@ bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const 
 void wgrad_split(int64_t M, int K, int N, int* splits, int* kb_per_split);
 int64_t wgrad_workspace_bytes(int64_t M, int K, int N);
 int wgrad_launch(const float* A, int64_t lda, const float* dH, int64_t ldh, float* out, int64_t M, int K, int N,
-                 int splits, int kb_per_split, cudaStream_t st);
+                 int splits, int kb_per_split, cudaStream_t st, const float* a_amax = nullptr, const float* b_amax = nullptr);
+bool wgrad_f16_ok(int K);
 }  // namespace tc
 }  // namespace gcs
 
@@ -473,10 +474,23 @@ extern "C" int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* d
   if (use_tc) {
     int splits, per;
     tc::wgrad_split(M, K, N, &splits, &per);
+    // fp16 split when the |max| of both operands is known (fused model) or, in debug mode 2, measured by an extra pass
+    const float* a_amax = amax_sink().consume_act;
+    const float* b_amax = amax_sink().consume;
+    if (!(a_amax && b_amax)) a_amax = b_amax = nullptr;
+    if (!a_amax && tc::f16_mode() == 2 && tc::wgrad_f16_ok(K)) {
+      static float* scratch = nullptr;                       // debug mode only: two cells, allocated once
+      if (!scratch) GCS_CUDA(cudaMalloc(&scratch, 256));
+      GCS_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(float), st));
+      GCS_TRY(tc::absmax(A, lda, M, K, scratch, st));
+      GCS_TRY(tc::absmax(dH, ldh, M, N, scratch + 1, st));
+      a_amax = scratch;
+      b_amax = scratch + 1;
+    }
     if (splits == 1) {
-      GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, dW, M, K, N, 1, per, st));
+      GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, dW, M, K, N, 1, per, st, a_amax, b_amax));
     } else {
-      GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, part, M, K, N, splits, per, st));
+      GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, part, M, K, N, splits, per, st, a_amax, b_amax));
       int64_t blocks = ceil_div(kn, 256);
       if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
       split_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(part, splits, kn, dW);

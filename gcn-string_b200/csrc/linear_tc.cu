@@ -854,10 +854,27 @@ constexpr uint32_t kWgPSmemBytes = kWgPStages * WGP_STAGE_BYTES + 1024 + 256;
 constexpr uint32_t kWgPairDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | (static_cast<uint32_t>(128 >> 3) << 17) |
                                  (static_cast<uint32_t>(256 >> 4) << 24);
 
+// fp16 variant (kF16): the same pipeline on kind::f16 MMAs, two K = 16 steps per 32-row block instead of four K = 8 steps.
+// A^T is packed two rows per 32-bit tensor-memory cell by the converters; the dH half slab lands RAW (one unswizzled
+// 32 x 64 fp32 box, 8 KB) and the splitter warps write its fp16 hi / 2^11-scaled lo parts (4 KB each) in the canonical
+// MN-major SWIZZLE_128B layout of 16-bit operands: 64 elements (128 B) along N per K row, 8-row groups 1024 B apart, the
+// 16-byte chunk index XORed with the row index inside the group.  Operand scales as in linear_tc_pair_kernel<true>.
+constexpr uint32_t kWgPairDescH = (1u << 4) | (1u << 16) | (static_cast<uint32_t>(128 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+__device__ __forceinline__ uint64_t make_mnmajor_f16_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1024 >> 4) << 16;                    // leading byte offset: next 64 columns (unused: N = 64 per CTA)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // stride byte offset: next 8 K rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+template <bool kF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad_tc_pair_kernel(
     const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
     float* __restrict__ out, int64_t out_split_stride, int ldo, int num_kb_total, int kb_per_split, int kWgChain,
-    int k_rows) {
+    int k_rows, const float* __restrict__ a_amax, const float* __restrict__ b_amax) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t bars = base + kWgPStages * WGP_STAGE_BYTES;
@@ -914,7 +931,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad
         mbar_arrive_expect_tx(full(s), WG_X_BYTES + WGP_Y_BYTES);
         tma_load_2d(xs, &map_x, i0, m, full(s));
         tma_load_2d(xs + WG_X_BYTES, &map_y, jh, m, full(s));
-        tma_load_2d(xs + WG_X_BYTES + 4096, &map_y, jh + 32, m, full(s));
+        if (!kF16) tma_load_2d(xs + WG_X_BYTES + 4096, &map_y, jh + 32, m, full(s));   // fp16: one raw 32 x 64 box
       }
     }
   } else if (warp == 1) {
@@ -929,16 +946,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad
         tc_fence_after();
         if (leader) {
           const uint32_t y_hi = base + s * WGP_STAGE_BYTES + WG_X_BYTES;
-          const uint64_t d_hi = make_mnmajor_b32_desc(y_hi);
-          const uint64_t d_lo = make_mnmajor_b32_desc(y_hi + WGP_Y_BYTES);
           const uint32_t a_hi = tmem_base + A_COL + t * 64;
+          if (kF16) {
+            const uint64_t d_hi = make_mnmajor_f16_desc(y_hi + WGP_Y_BYTES);          // fp16 hi behind the raw slab, lo behind it
+            const uint64_t d_lo = make_mnmajor_f16_desc(y_hi + WGP_Y_BYTES + 4096);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t koff = static_cast<uint64_t>((k * 8 * 128) >> 4);       // 8 rows of 128 B per K step
-            const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
-            mma_tf32_ts_pair(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kWgPairDesc, acc);
-            mma_tf32_ts_pair(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kWgPairDesc, acc);
-            mma_tf32_ts_pair(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kWgPairDesc, 1u);
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * 2048) >> 4);          // 16 rows = two 8-row groups per K step
+              const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
+              mma_f16_ts_pair(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kWgPairDescH, acc);
+              mma_f16_ts_pair(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kWgPairDescH, acc);
+              mma_f16_ts_pair(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kWgPairDescH, 1u);
+            }
+          } else {
+            const uint64_t d_hi = make_mnmajor_b32_desc(y_hi);
+            const uint64_t d_lo = make_mnmajor_b32_desc(y_hi + WGP_Y_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * 8 * 128) >> 4);       // 8 rows of 128 B per K step
+              const uint32_t acc = (pos > 0 || k > 0) ? 1u : 0u;
+              mma_tf32_ts_pair(tmem_base + ACC_MAIN, a_hi + k * 8, d_hi + koff, kWgPairDesc, acc);
+              mma_tf32_ts_pair(tmem_base + ACC_CORR, a_hi + k * 8, d_lo + koff, kWgPairDesc, acc);
+              mma_tf32_ts_pair(tmem_base + ACC_CORR, a_hi + 32 + k * 8, d_hi + koff, kWgPairDesc, 1u);
+            }
           }
           tc_commit_pair(smem_empty(s));
           tc_commit_pair(a_empty(t));
@@ -952,22 +982,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad
     const int quarter = warp & 3;
     const int i = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const float a_scale = kF16 ? f16_scale(__ldg(a_amax)) : 1.f;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % kWgPStages, t = kb % kWgAStages;
       mbar_wait(full(s), (kb / kWgPStages) & 1);
       const uint32_t xs = base + s * WGP_STAGE_BYTES;
       uint32_t hi[32], lo[32];
+      if (kF16) {
 #pragma unroll
-      for (int m = 0; m < 32; ++m) {
-        float v;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (m * 128 + i) * 4));
-        split_tf32(v, hi[m], lo[m]);
+        for (int m = 0; m < 16; ++m) {                         // rows 2m, 2m+1 of the slab share one tensor-memory cell
+          float v0, v1;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(xs + ((2 * m) * 128 + i) * 4));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(xs + ((2 * m + 1) * 128 + i) * 4));
+          split_f16x2(v0 * a_scale, v1 * a_scale, hi[m], lo[m]);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xs + (m * 128 + i) * 4));
+          split_tf32(v, hi[m], lo[m]);
+        }
       }
       mbar_wait(a_empty(t), ((kb / kWgAStages) & 1) ^ 1);
       tc_fence_after();
       const uint32_t a_hi = tmem_base + lane_addr + A_COL + t * 64;
-      tmem_st32(a_hi, hi);
-      tmem_st32(a_hi + 32, lo);
+      if (kF16) {
+        tmem_st16(a_hi, *reinterpret_cast<const uint32_t(*)[16]>(hi));
+        tmem_st16(a_hi + 32, *reinterpret_cast<const uint32_t(*)[16]>(lo));
+      } else {
+        tmem_st32(a_hi, hi);
+        tmem_st32(a_hi + 32, lo);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -977,10 +1023,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad
     // ------------------------------------------------------------ dH splitters: this CTA's 64 columns, hi in place,
     // lo into the two boxes right behind
     const int ct = (warp - 6) * 32 + lane;
+    const float b_scale = kF16 ? f16_scale(__ldg(b_amax)) : 1.f;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % kWgPStages;
       mbar_wait(full(s), (kb / kWgPStages) & 1);
       const uint32_t ys = base + s * WGP_STAGE_BYTES + WG_X_BYTES;
+      if (kF16) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int q = ct + 128 * u;                          // 32 rows x 8 chunks of 8 columns
+          const int row = q >> 3, ch = q & 7;
+          float4 v0, v1;
+          const uint32_t src = ys + row * 256 + ch * 32;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(src + 16));
+          uint32_t h4[4], l4[4];
+          split_f16x2(v0.x * b_scale, v0.y * b_scale, h4[0], l4[0]);
+          split_f16x2(v0.z * b_scale, v0.w * b_scale, h4[1], l4[1]);
+          split_f16x2(v1.x * b_scale, v1.y * b_scale, h4[2], l4[2]);
+          split_f16x2(v1.z * b_scale, v1.w * b_scale, h4[3], l4[3]);
+          const uint32_t dst = ys + WGP_Y_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h4[0]), "r"(h4[1]), "r"(h4[2]), "r"(h4[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4096), "r"(l4[0]), "r"(l4[1]), "r"(l4[2]), "r"(l4[3]) : "memory");
+        }
+      } else
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t addr = ys + (ct + 128 * u) * 16;
@@ -1002,6 +1068,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int num_chains = (num_kb + kWgChain - 1) / kWgChain;
+    const float out_scale = kF16 ? (1.f / f16_scale(__ldg(a_amax))) * (1.f / f16_scale(__ldg(b_amax))) : 1.f;
     for (int chain = 0; chain < num_chains; ++chain) {
       mbar_wait(acc_full, chain & 1);
       tc_fence_after();
@@ -1015,8 +1082,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1) wgrad
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-          float x = __uint_as_float(v[q]) + __uint_as_float(w[q]);
+          float x = kF16 ? fmaf(__uint_as_float(w[q]), 1.f / 2048.f, __uint_as_float(v[q])) : __uint_as_float(v[q]) + __uint_as_float(w[q]);
           if (chain > 0) x += __uint_as_float(run[q]);
+          if (kF16 && last) x *= out_scale;                    // undo the operand scales (powers of two)
           run[q] = __float_as_uint(x);
         }
         if (!last) {
@@ -1222,6 +1290,8 @@ bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const 
          M < (1LL << 31) - 64;
 }
 
+static int g_wg_f16 = 1;                                 // debug knob (gcs_debug_set_param 9): 0 = weight gradient on the tf32 split only
+void set_wgrad_f16(int v) { g_wg_f16 = v; }
 static int g_wg_pair = 1;                                // debug knob: 0 = always the one-CTA kernel
 void set_wgrad_pair(int v) { g_wg_pair = v; }
 static bool wgrad_use_pair(int K) { return g_wg_pair && K % 256 == 0; }
@@ -1254,20 +1324,32 @@ int64_t wgrad_workspace_bytes(int64_t M, int K, int N) {
 }
 
 // partials: [splits][K][N]; with one split the result goes straight to dW (ld = N).
+bool wgrad_f16_ok(int K) { return g_f16 != 0 && g_wg_f16 != 0 && wgrad_use_pair(K); }
+
+// a_amax / b_amax: device |max| of A and dH (both or neither): the fp16 variant of the pair kernel.
 int wgrad_launch(const float* A, int64_t lda, const float* dH, int64_t ldh, float* out, int64_t M, int K, int N,
-                 int splits, int kb_per_split, cudaStream_t st) {
+                 int splits, int kb_per_split, cudaStream_t st, const float* a_amax, const float* b_amax) {
   alignas(64) CUtensorMap mx, my;
   GCS_TRY(make_map(&mx, A, M, K, lda, 32, 128, CU_TENSOR_MAP_SWIZZLE_NONE));
-  GCS_TRY(make_map(&my, dH, M, N, ldh, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  const bool f16 = a_amax && b_amax && wgrad_f16_ok(K);
+  if (f16) GCS_TRY(make_map(&my, dH, M, N, ldh, 32, 64, CU_TENSOR_MAP_SWIZZLE_NONE));      // raw 32 x 64 slab halves
+  else GCS_TRY(make_map(&my, dH, M, N, ldh, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   if (wgrad_use_pair(K)) {
     static bool attr2 = false;
     if (!attr2) {
-      GCS_CUDA(cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgPSmemBytes));
+      GCS_CUDA(cudaFuncSetAttribute(wgrad_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgPSmemBytes));
+      GCS_CUDA(cudaFuncSetAttribute(wgrad_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgPSmemBytes));
       attr2 = true;
     }
     dim3 grid(static_cast<unsigned>(2 * (K / 256)), N / 128, splits);       // x = 2 * tile + rank in the pair
-    wgrad_tc_pair_kernel<<<grid, kWgThreads, kWgPSmemBytes, st>>>(mx, my, out, static_cast<int64_t>(K) * N, N,
-                                                                static_cast<int>(ceil_div(M, 32)), kb_per_split, g_wg_chain, K);
+    if (f16)
+      wgrad_tc_pair_kernel<true><<<grid, kWgThreads, kWgPSmemBytes, st>>>(mx, my, out, static_cast<int64_t>(K) * N, N,
+                                                                        static_cast<int>(ceil_div(M, 32)), kb_per_split,
+                                                                        g_wg_chain, K, a_amax, b_amax);
+    else
+      wgrad_tc_pair_kernel<false><<<grid, kWgThreads, kWgPSmemBytes, st>>>(mx, my, out, static_cast<int64_t>(K) * N, N,
+                                                                         static_cast<int>(ceil_div(M, 32)), kb_per_split,
+                                                                         g_wg_chain, K, nullptr, nullptr);
     GCS_CHECK_LAUNCH("wgrad_tc_pair_kernel");
     return GCS_OK;
   }

@@ -140,9 +140,10 @@ struct Plan {
 // Sets the thread's AmaxSink for the calls inside a scope (see common.cuh: feeds the fp16 tensor-core GEMMs).
 struct AmaxScope {
   AmaxSink saved;
-  AmaxScope(float* produce, const float* consume) : saved(amax_sink()) {
+  AmaxScope(float* produce, const float* consume, const float* consume_act = nullptr) : saved(amax_sink()) {
     amax_sink().produce = produce;
     amax_sink().consume = consume;
+    amax_sink().consume_act = consume_act;
   }
   ~AmaxScope() { amax_sink() = saved; }
 };
@@ -381,7 +382,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
     da = din;
     ldda = lddin;
   }
-  AmaxScope node_scope(nullptr, p.amax + 1);
+  AmaxScope node_scope(nullptr, p.amax + 1, p.amax);        // weight gradients: activations under amax[0], dh under amax[1]
   // ---- message passing, last layer first.  Block z_k of cat (columns [(L-1-k)H, (L-k)H)) is read by
   // the pool and by every later conv layer k' > k (rows [(k'-1-k)H, (k'-k)H) of its kernel).
   const int64_t ldd = static_cast<int64_t>(L) * H;
@@ -462,6 +463,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
   da = da_pre;
   ldda = ldda_pre;
   for (int j = P - 1; j >= 0; --j) {
+    if (j == 0) amax_sink().consume_act = nullptr;           // the raw features are not covered by amax[0]
     const float* in = j == 0 ? bt.x : p.act[j - 1];
     const int64_t ld_in = j == 0 ? bt.ldx : H;
     GCS_TRY(block_backward(c, p, j, params, grads, da, ldda, p.h[j], H, N, in, ld_in, p.tmp_b, H,

@@ -292,7 +292,7 @@ int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 whenever supplie
 
 // Test / sweep hook (not part of the drop-in surface).
 extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
-namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); void set_wgrad_pair(int v); void set_f16_mode(int v); void set_max_chain_k_f16(int k); } }
+namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); void set_wgrad_pair(int v); void set_f16_mode(int v); void set_max_chain_k_f16(int k); void set_wgrad_f16(int v); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
   if (id == 2 && value > 0) g_rb4_iters = value;
@@ -301,6 +301,7 @@ extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 4) gcs::tc::set_wgrad_pair(value);
   if (id == 7) gcs::tc::set_f16_mode(value);             // 0 tf32 only, 1 fp16 inside the fused model, 2 fp16 everywhere
   if (id == 8) gcs::tc::set_max_chain_k_f16(value);
+  if (id == 9) gcs::tc::set_wgrad_f16(value);                // 0 = weight gradient on the tf32 split only
 }
 
 extern "C" int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows) {

@@ -175,6 +175,57 @@ def test_tensor_core_gemms_forced(M, K, N):
         lib.gcs_debug_set_gemm_mode(0)
 
 
+@pytest.mark.parametrize("M,K,N", [(1, 256, 128), (255, 128, 256), (257, 384, 128), (511, 2048, 256), (33000, 1280, 256)])
+@pytest.mark.parametrize("scaling", ["unit", "tiny", "huge", "spread"])
+def test_fp16_split_tensor_core_gemm(M, K, N, scaling):
+    """linear_tc_pair_kernel<true> (3 kind::f16 MMAs per product on fp16 hi / 2^11-scaled lo operands, power-of-two
+    operand scales from the |max|) through the standalone ops in debug mode 2: fp32-level accuracy against float64 for
+    unit-scale operands, for operands far outside fp16's exponent range (gradients ~1e-9, activations ~3e4) and for a
+    2^24 spread inside one operand; ragged rows, strided operands, chunked reductions, accumulate, determinism."""
+    lib = _lib.load()
+    rng = np.random.default_rng(M + K + N + len(scaling))
+    a_mag, w_mag = {"unit": (1.0, 1.0), "tiny": (1e-9, 1e-4), "huge": (3e4, 50.0), "spread": (1.0, 1.0)}[scaling]
+    wideA = (rng.standard_normal((M, K + 64)) * a_mag).astype(np.float32)
+    if scaling == "spread":
+        wideA *= np.exp2(-rng.integers(0, 25, wideA.shape)).astype(np.float32)
+    A = wideA[:, 32:32 + K]
+    W = (rng.standard_normal((K, N)) / np.sqrt(K) * w_mag).astype(np.float32)
+    b = (rng.standard_normal(N) * a_mag * w_mag).astype(np.float32)
+    dH = (rng.standard_normal((M, N)) * a_mag).astype(np.float32)
+    A64, W64, dH64 = A.astype(np.float64), W.astype(np.float64), dH.astype(np.float64)
+    dA = dev(wideA)[:, 32:32 + K]
+    try:
+        lib.gcs_debug_set_param(7, 2)
+        lib.gcs_debug_set_gemm_mode(2)
+        out = torch.zeros(M, N + 128, device="cuda")
+        y = ops.linear_fwd(dA, dev(W), dev(b), out=out[:, 128:])
+        assert rel_err(host(y), A64 @ W64 + b) < TOL and float(out[:, :128].abs().max()) == 0.0
+        assert torch.equal(ops.linear_fwd(dA, dev(W), dev(b)), y.contiguous())
+        base = (rng.standard_normal((M, K)) * a_mag * w_mag).astype(np.float32)
+        acc = ops.linear_bwd_input(dev(dH), dev(W), out=dev(base), accumulate=True)
+        assert rel_err(host(acc), base + dH64 @ W64.T) < TOL
+        if K % 256 == 0:                                                    # weight gradient: the fp16 CTA-pair kernel
+            dW, _ = ops.linear_bwd_weight(dA, dev(dH), want_db=False)
+            assert rel_err(host(dW), A64.T @ dH64) < TOL
+            dW2, _ = ops.linear_bwd_weight(dA, dev(dH), want_db=False)
+            assert torch.equal(dW, dW2)
+        lib.gcs_debug_set_param(7, 0)                                       # the tf32 kernel on the same operands
+        y_tf32 = ops.linear_fwd(dA, dev(W), dev(b))
+        assert rel_err(host(y_tf32), A64 @ W64 + b) < TOL
+    finally:
+        lib.gcs_debug_set_gemm_mode(0)
+        lib.gcs_debug_set_param(7, 1)
+    # all-zero operand: the scale falls back to 1
+    try:
+        lib.gcs_debug_set_param(7, 2)
+        lib.gcs_debug_set_gemm_mode(2)
+        z = ops.linear_fwd(torch.zeros(M, K, device="cuda"), dev(W), dev(b))
+        assert rel_err(host(z), np.broadcast_to(b, (M, N))) < TOL
+    finally:
+        lib.gcs_debug_set_gemm_mode(0)
+        lib.gcs_debug_set_param(7, 1)
+
+
 def test_linear_on_strided_views_of_the_concat_buffer():
     rng = np.random.default_rng(9)
     cat = dev(rng.standard_normal((500, 5 * 64)).astype(np.float32))
