@@ -257,7 +257,7 @@ def run_b200(args):
                     "traffic_source": "profiles/r01_spmm_rb4_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": t * 1e6,
                     "edges_per_sec": nnz / t, "frac_of_nominal_8TBs": ach / 8000.0}
-    # the time-dominant kernels are the dense transforms (3xTF32 on tcgen05): fp32-equivalent rate of the forward GEMMs
+    # the time-dominant kernels are the dense transforms (error-compensated fp16 split on tcgen05): fp32-equivalent rate of the forward GEMMs
     if "linear_fwd" in prof:
         cnt, ms = prof["linear_fwd"]
         steps_prof = 2

@@ -100,10 +100,13 @@ int gcs_cast_f64_f32(const double* src, float* dst, int64_t n, gcs_stream stream
  *   bwd_weight: dW[K,N] = A[M,K]^T . dH[M,N];  db[N] = colsum(dH)   (db may be NULL)
  *               workspace: gcs_linear_bwd_weight_workspace_bytes(M,K,N)
  *   bwd_input:  dA[M,K] (+)= dH[M,N] . W[K,N]^T               (accumulate != 0 adds)
- * fwd / bwd_input run on the tensor cores (tcgen05, 3xTF32 split, fp32-accurate) when the
+ * fwd / bwd_input run on the tensor cores (tcgen05; error-compensated operand splits, fp32-accurate) when the
  * reduction width is a multiple of 32, the output width a multiple of 128 and a workspace
  * of gcs_linear_workspace_bytes(M,K,N) is given (it holds the split weights); otherwise, or
- * with workspace == NULL, on the CUDA cores (exact fp32 FFMA).
+ * with workspace == NULL, on the CUDA cores (exact fp32 FFMA).  These standalone entry points use the 3 x TF32
+ * split; inside gcs_model_forward / gcs_model_train_step, where the producer kernels maintain the |max| of every
+ * activation / gradient tensor, the same transforms run as 3 x FP16 products (hi + 2^11-scaled lo, power-of-two
+ * operand scales) at twice the MMA rate with the same 22-bit operand precision.
  * --------------------------------------------------------------------------------- */
 int64_t gcs_linear_workspace_bytes(int64_t M, int32_t K, int32_t N);
 int gcs_linear_fwd(const float* A, int64_t lda, const float* W, const float* bias, float* C,
