@@ -273,7 +273,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : k
     const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_c,
     const float* __restrict__ bias, int64_t M, int K, int n_tiles, int num_tiles, int accumulate,
     const float* __restrict__ rowbias, int64_t ld_rowbias, const int64_t* __restrict__ seg,
-    const float* __restrict__ a_amax, const float* __restrict__ b_scale_inv) {
+    const float* __restrict__ a_amax, const float* __restrict__ b_scale_inv, const float* __restrict__ alpha,
+    float* __restrict__ amax_out) {
   constexpr int kPStages = kF16 ? kHStages : tc::kPStages;
   constexpr uint32_t P_STAGE_BYTES = kF16 ? H_STAGE_BYTES : tc::P_STAGE_BYTES;
   constexpr uint32_t A_BYTES = kF16 ? 2 * A_RAW_BYTES : A_RAW_BYTES;
@@ -394,7 +395,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : k
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t it = 0, tile_iter = 0;
-    float a_scale = 1.f, out_scale = 1.f;
+    float a_scale = 1.f, out_scale = 1.f, out_max = 0.f;
     if (kF16) {
       a_scale = f16_scale(__ldg(a_amax));
       out_scale = (1.f / a_scale) * __ldg(b_scale_inv);       // powers of two: exact
@@ -488,6 +489,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : k
               const float4 b = __ldg(reinterpret_cast<const float4*>(rb + c0) + qq);
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
+            if (alpha) {                                     // inference: BatchNorm is folded into W / bias, PReLU here
+              const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + n0 + c0) + qq);
+              o.x = o.x > 0.f ? o.x : al.x * o.x; o.y = o.y > 0.f ? o.y : al.y * o.y;
+              o.z = o.z > 0.f ? o.z : al.z * o.z; o.w = o.w > 0.f ? o.w : al.w * o.w;
+            }
+            if (amax_out && row < M) out_max = amax4(out_max, o);
             const uint32_t dst = sbuf + lane * 128 + ((qq ^ (lane & 7)) << 4);          // SWIZZLE_128B box layout
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
           }
@@ -545,6 +552,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : k
       tc_fence_before();          // accumulator reads ordered before this warp's next a_ready arrive
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");           // every box written before the CTA exits
+    if (kF16) amax_commit(out_max, amax_out);
   }
   tc_fence_before();
   cluster_sync_all();              // the peer's tensor core may still read this CTA's shared memory until its commits land
@@ -575,13 +583,27 @@ __global__ void __launch_bounds__(256) split_weights_kernel(const float* __restr
 }
 
 // |max| of a strided matrix into *cell (pre-zeroed; non-negative floats order like their bit patterns).
-__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int K, float* cell) {
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int K, float* cell,
+                                                     const float* __restrict__ col_scale) {
   float m = 0.f;
   for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
     const float* row = A + r * lda;
-    for (int c = threadIdx.x; c < K; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(row + c)));
+    for (int c = threadIdx.x; c < K; c += blockDim.x)
+      m = fmaxf(m, fabsf(col_scale ? __ldg(row + c) * __ldg(col_scale + c) : __ldg(row + c)));
   }
   amax_commit(m, cell);
+}
+
+// Inference fold of BatchNorm into the bias of the dense layer in front of it: b' = b * scale + shift.
+__global__ void fold_bias_kernel(const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) out[n] = fmaf(bias ? bias[n] : 0.f, scale[n], shift[n]);
+}
+
+// cell = max(cell, other): joins the |max| a fused GEMM produced into the running maximum it read its own scale from.
+__global__ void amax_merge_kernel(float* cell, const float* other) {
+  if (*other > *cell) *cell = *other;
 }
 
 // fp16 split of the weights for linear_tc_pair_kernel<true>: hi = fp16(w * s), lo = fp16((w * s - hi) * 2^11) with
@@ -589,14 +611,16 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A
 __global__ void __launch_bounds__(256) split_weights_f16_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
                                                                 int transpose, int64_t ldo, __half* __restrict__ hi,
                                                                 __half* __restrict__ lo, const float* __restrict__ amax,
-                                                                float* __restrict__ scale_inv) {
+                                                                float* __restrict__ scale_inv,
+                                                                const float* __restrict__ col_scale) {
   const float s = f16_scale(__ldg(amax));
   if (blockIdx.x == 0 && threadIdx.x == 0) *scale_inv = 1.f / s;
   const int64_t n = static_cast<int64_t>(rows) * cols;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<int64_t>(r) * cols);
-    const float y = __ldg(W + r * ldw + c) * s;
+    const float w = col_scale ? __ldg(W + r * ldw + c) * __ldg(col_scale + c) : __ldg(W + r * ldw + c);
+    const float y = w * s;
     const __half h = __float2half_rn(y);
     const int64_t o = transpose ? c * ldo + r : r * ldo + c;
     hi[o] = h;
@@ -1209,7 +1233,7 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
     const bool first = k0 == 0;
     linear_tc_pair_kernel<false><<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
                                                                       first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
-                                                                      seg, nullptr, nullptr);
+                                                                      seg, nullptr, nullptr, nullptr, nullptr);
     GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
   }
   return GCS_OK;
@@ -1221,6 +1245,7 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
 static int g_f16 = 1;      // 0 = tf32 kernels only, 1 = fp16 where the caller knows the A operand's |max|, 2 = fp16 everywhere (|max| by an extra pass)
 void set_f16_mode(int v) { if (v >= 0 && v <= 2) g_f16 = v; }
 int f16_mode() { return g_f16; }
+int f16_max_chain() { return g_max_chain_k_f16; }
 bool f16_shape_ok(int K) { return K % BKH == 0; }
 float* f16_cells(void* workspace, int K, int N) {
   return reinterpret_cast<float*>(static_cast<char*>(workspace) + round_up(4LL * K * N, 256));
@@ -1231,21 +1256,31 @@ int f16_begin(float* cells, cudaStream_t st) {
   GCS_CUDA(cudaMemsetAsync(cells, 0, 3 * sizeof(float), st));
   return GCS_OK;
 }
-int absmax(const float* A, int64_t lda, int64_t M, int K, float* cell, cudaStream_t st) {
+int absmax(const float* A, int64_t lda, int64_t M, int K, float* cell, cudaStream_t st, const float* col_scale) {
   int64_t blocks = M < 8LL * sm_count() ? M : 8LL * sm_count();
   if (blocks < 1) blocks = 1;
-  absmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(A, lda, M, K, cell);
+  absmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(A, lda, M, K, cell, col_scale);
   GCS_CHECK_LAUNCH("absmax_kernel");
   return GCS_OK;
 }
+int fold_bias(const float* bias, const float* scale, const float* shift, int N, float* out, cudaStream_t st) {
+  fold_bias_kernel<<<static_cast<unsigned>(ceil_div(N, 128)), 128, 0, st>>>(bias, scale, shift, N, out);
+  GCS_CHECK_LAUNCH("fold_bias_kernel");
+  return GCS_OK;
+}
+int amax_merge(float* cell, const float* other, cudaStream_t st) {
+  amax_merge_kernel<<<1, 1, 0, st>>>(cell, other);
+  GCS_CHECK_LAUNCH("amax_merge_kernel");
+  return GCS_OK;
+}
 int split_f16_strided(const float* W, int rows, int cols, int64_t ldw, bool transpose, int64_t ldo, void* hi, void* lo,
-                      float* cells, cudaStream_t st) {
+                      float* cells, cudaStream_t st, const float* col_scale) {
   const int64_t n = static_cast<int64_t>(rows) * cols;
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
   split_weights_f16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(W, rows, cols, ldw, transpose ? 1 : 0, ldo,
                                                                         static_cast<__half*>(hi), static_cast<__half*>(lo),
-                                                                        cells, cells + 1);
+                                                                        cells, cells + 1, col_scale);
   GCS_CHECK_LAUNCH("split_weights_f16_kernel");
   return GCS_OK;
 }
@@ -1253,7 +1288,9 @@ int split_f16_strided(const float* W, int rows, int cols, int64_t ldw, bool tran
 // Bt: fp16 split weights [N][K] (hi, lo), cells as left by split_f16_strided; a_amax: device |max| of A.
 int launch_f16(const float* A, int64_t lda, const void* Bt_hi, const void* Bt_lo, const float* cells, const float* a_amax,
                const float* bias, float* C, int64_t ldc, int64_t M, int K, int N, int accumulate, cudaStream_t st,
-               const float* rowbias, int64_t ld_rowbias, const int64_t* seg) {
+               const float* rowbias, int64_t ld_rowbias, const int64_t* seg, const float* alpha, float* amax_out) {
+  if ((alpha || amax_out) && K > g_max_chain_k_f16)
+    return fail(GCS_ERR_UNSUPPORTED, "launch_f16: the PReLU / |max| epilogue needs the reduction in one chain");
   alignas(64) CUtensorMap ma, mh, ml, mc;
   GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));
   static bool attr = false;
@@ -1277,7 +1314,7 @@ int launch_f16(const float* A, int64_t lda, const void* Bt_hi, const void* Bt_lo
     const bool first = k0 == 0;
     linear_tc_pair_kernel<true><<<grid, kHThreads, kHSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
                                                                      first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
-                                                                     seg, a_amax, cells + 1);
+                                                                     seg, a_amax, cells + 1, alpha, amax_out);
     GCS_CHECK_LAUNCH("linear_tc_pair_kernel<f16>");
   }
   return GCS_OK;

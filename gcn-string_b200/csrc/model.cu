@@ -33,6 +33,11 @@ int dense_dx_concat(const float* dh, int64_t ld, const float* const* W, const in
                     int n_graphs, float* C, int64_t ldc, int64_t M, int accumulate, void* workspace,
                     int64_t workspace_bytes, cudaStream_t st);
 
+int linear_fwd_bn_prelu(const float* A, int64_t lda, const float* W, const float* bias, const float* scale,
+                        const float* shift, const float* alpha, float* C, int64_t ldc, int64_t M, int K, int N,
+                        void* workspace, int64_t workspace_bytes, float* amax_out, cudaStream_t st, int* used);
+namespace tc { int amax_merge(float* cell, const float* other, cudaStream_t st); }
+
 struct BlockDesc {
   int k_in, m_out;
   bool has_alpha;
@@ -275,12 +280,24 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
   for (int j = 0; j < P; ++j) {
     const BlockDesc& b = p.blocks[j];
     amax_sink().consume = j > 0 ? p.amax : nullptr;
-    GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
-    GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
     float* out = j < P - 1 ? p.act[j] : emb(0);
     const int64_t ld_out = j < P - 1 ? H : ld_emb;
     const float* scale = p.stat[j] + 2 * H;
-    GCS_TIMED("bn_prelu_fwd", gcs_bn_prelu_fwd(p.h[j], H, scale, scale + H, params + b.alpha(), out, ld_out, N, H, st));
+    int fused = 0;
+    if (!training) {
+      // inference: moving-statistics BatchNorm folded into the GEMM, PReLU in its epilogue (one pass instead of three);
+      // the |max| of the result goes through a scratch cell so that the GEMM does not raise the cell it reads
+      GCS_TRY(block_norm(c, p, j, params, state, nullptr, H, N, false, st));
+      GCS_TIMED("linear_fwd", linear_fwd_bn_prelu(in, ld_in, params + b.kernel(), params + b.bias(), scale, scale + H,
+                                                  params + b.alpha(), out, ld_out, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes,
+                                                  p.amax + 2, as_stream(st), &fused));
+      if (fused) GCS_TRY(tc::amax_merge(p.amax, p.amax + 2, as_stream(st)));
+    }
+    if (!fused) {
+      GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
+      GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
+      GCS_TIMED("bn_prelu_fwd", gcs_bn_prelu_fwd(p.h[j], H, scale, scale + H, params + b.alpha(), out, ld_out, N, H, st));
+    }
     in = out;
     ld_in = ld_out;
   }
@@ -290,9 +307,23 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     const int bi = P + k;
     const BlockDesc& b = p.blocks[bi];
     const float* cin = emb(k);
+    const float* scale = p.stat[bi] + 2 * H;
+    int fused = 0;
+    if (!training) {
+      // inference: p.h[bi] receives prelu(bn(out . W + b)) straight from the GEMM; the aggregation is a plain gather
+      GCS_TRY(block_norm(c, p, bi, params, state, nullptr, H, N, false, st));
+      GCS_TIMED("linear_fwd", linear_fwd_bn_prelu(cin, ld_emb, params + b.kernel(), params + b.bias(), scale, scale + H,
+                                                  params + b.alpha(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes,
+                                                  nullptr, as_stream(st), &fused));
+    }
+    if (fused) {
+      GCS_TIMED("spmm_fwd", gcs_spmm_aggregate(bt.rowptr, bt.colidx, nullptr, bt.rb4_blk_ptr, bt.rb4_ent, N, p.h[bi], H,
+                                               nullptr, nullptr, nullptr, c.connectivity == 2 ? emb(k) : nullptr, H,
+                                               emb(k + 1), ld_emb, H, 0, st));
+      continue;
+    }
     GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, ld_emb, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
-    const float* scale = p.stat[bi] + 2 * H;
     // z_k is the leading block of out_{k+1} ('cat'), or out_{k+1} = z_k (+ out_k for 'sum') in the next slab
     GCS_TIMED("spmm_fwd", gcs_spmm_aggregate(bt.rowptr, bt.colidx, nullptr, bt.rb4_blk_ptr, bt.rb4_ent, N,
                                              p.h[bi], H, scale, scale + H, params + b.alpha(),
