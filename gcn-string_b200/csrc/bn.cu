@@ -131,6 +131,23 @@ __global__ void __launch_bounds__(256) bn_stats_final_kernel(const double* __res
   }
 }
 
+// Statistics out of the dense layer's own epilogue (linear_tc.cu writes, per group of 32 rows and per column, the fp32
+// pair {sum h, sum h^2}): fold the groups into the same per-split fp64 partials the pass over h would have produced.
+__global__ void __launch_bounds__(256) bn_stats_from_part_kernel(const float2* __restrict__ part, int64_t groups, int C,
+                                                                 int splits, double* __restrict__ ws) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double acc[2] = {0.0, 0.0};
+  if (c < C) {
+    for (int64_t g = static_cast<int64_t>(blockIdx.y) * 8 + warp; g < groups; g += 8LL * splits) {
+      const float2 v = __ldg(part + g * C + c);
+      acc[0] += static_cast<double>(v.x);
+      acc[1] += static_cast<double>(v.y);
+    }
+  }
+  block_store_partials<2>(acc, ws + (static_cast<int64_t>(blockIdx.y) * C + c) * 2, 0, 0, c < C);
+}
+
 // Synchronised BatchNorm: the per-column sums of this rank (+ its row count as the last element) go through the
 // all-reduce hook, mean / variance are formed from the global sums.
 __global__ void __launch_bounds__(256) bn_stats_sums_kernel(const double* __restrict__ ws, int splits, int C, int64_t M,
@@ -493,6 +510,46 @@ extern "C" int64_t gcs_bn_workspace_bytes(int64_t M, int32_t C) {
          round_up(4LL * C * sizeof(float), 256) + round_up((3LL * C + 1) * sizeof(double), 256);   // partials | coef | sync sums
 }
 
+// Per-split fp64 partials -> mean / biased variance (through the synchronised-BatchNorm hook when one is installed).
+static int bn_stats_finish(const double* ws, int splits, int C, int64_t M, float* mean, float* var, void* workspace,
+                           gcs_stream stream) {
+  cudaStream_t st = as_stream(stream);
+  const SyncHook& hook = sync_hook();
+  if (hook.fn) {
+    double* sums = reinterpret_cast<double*>(static_cast<char*>(workspace) +
+                                             round_up(bn_max_splits(M) * C * 3 * static_cast<int64_t>(sizeof(double)), 256) +
+                                             round_up(4LL * C * sizeof(float), 256));
+    bn_stats_sums_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, splits, C, M, sums);
+    GCS_CHECK_LAUNCH("bn_stats_sums_kernel");
+    if (hook.fn(sums, 2LL * C + 1, stream, hook.user) != 0) return fail(GCS_ERR_CUDA, "gcs_bn_stats: the all-reduce hook failed");
+    bn_stats_finish_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(sums, C, mean, var);
+    GCS_CHECK_LAUNCH("bn_stats_finish_kernel");
+    return GCS_OK;
+  }
+  bn_stats_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, splits, C, M, mean, var);
+  GCS_CHECK_LAUNCH("bn_stats_final_kernel");
+  return GCS_OK;
+}
+
+namespace gcs {
+// part: [ceil(M/32)][C] float2 written by the dense layer's epilogue (rows >= M excluded there).
+int bn_stats_from_partials(const float* part, int64_t M, int C, float* mean, float* var, void* workspace,
+                           int64_t workspace_bytes, gcs_stream stream) {
+  if (workspace_bytes < gcs_bn_workspace_bytes(M, C)) return fail(GCS_ERR_WORKSPACE, "bn_stats_from_partials: workspace too small");
+  const int64_t groups = ceil_div(M, 32);
+  int64_t splits = ceil_div(groups, 64);                     // >= 8 groups per warp
+  const int64_t cap = bn_max_splits(M) < 64 ? bn_max_splits(M) : 64;
+  if (splits > cap) splits = cap;
+  if (splits < 1) splits = 1;
+  double* ws = static_cast<double*>(workspace);
+  dim3 grid(static_cast<unsigned>(ceil_div(C, 32)), static_cast<unsigned>(splits));
+  bn_stats_from_part_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(part), groups, C,
+                                                                static_cast<int>(splits), ws);
+  GCS_CHECK_LAUNCH("bn_stats_from_part_kernel");
+  return bn_stats_finish(ws, static_cast<int>(splits), C, M, mean, var, workspace, stream);
+}
+}  // namespace gcs
+
 extern "C" int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, float* mean, float* var,
                             void* workspace, int64_t workspace_bytes, gcs_stream stream) {
   GCS_CHECK_ARG(M > 0 && C > 0, "gcs_bn_stats: needs at least one row (M=%lld, C=%d)", (long long)M, C);
@@ -508,21 +565,7 @@ extern "C" int gcs_bn_stats(const float* h, int64_t ldh, int64_t M, int32_t C, f
   if (vec) bn_stats_partial_kernel<4><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
   else bn_stats_partial_kernel<1><<<grid, kBnThreads, 0, st>>>(h, ldh, M, C, g.rows_per_split, ws);
   GCS_CHECK_LAUNCH("bn_stats_partial_kernel");
-  const SyncHook& hook = sync_hook();
-  if (hook.fn) {
-    double* sums = reinterpret_cast<double*>(static_cast<char*>(workspace) +
-                                             round_up(bn_max_splits(M) * C * 3 * static_cast<int64_t>(sizeof(double)), 256) +
-                                             round_up(4LL * C * sizeof(float), 256));
-    bn_stats_sums_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, sums);
-    GCS_CHECK_LAUNCH("bn_stats_sums_kernel");
-    if (hook.fn(sums, 2LL * C + 1, stream, hook.user) != 0) return fail(GCS_ERR_CUDA, "gcs_bn_stats: the all-reduce hook failed");
-    bn_stats_finish_kernel<<<static_cast<unsigned>(ceil_div(C, 128)), 128, 0, st>>>(sums, C, mean, var);
-    GCS_CHECK_LAUNCH("bn_stats_finish_kernel");
-    return GCS_OK;
-  }
-  bn_stats_final_kernel<<<static_cast<unsigned>(ceil_div(C, 8)), 256, 0, st>>>(ws, g.splits, C, M, mean, var);
-  GCS_CHECK_LAUNCH("bn_stats_final_kernel");
-  return GCS_OK;
+  return bn_stats_finish(ws, g.splits, C, M, mean, var, workspace, stream);
 }
 
 extern "C" int gcs_bn_fold(const float* mean, const float* var, const float* gamma, const float* beta,

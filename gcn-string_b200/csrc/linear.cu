@@ -277,7 +277,7 @@ int split_f16_strided(const float* W, int rows, int cols, int64_t ldw, bool tran
 int launch_f16(const float* A, int64_t lda, const void* Bt_hi, const void* Bt_lo, const float* cells, const float* a_amax,
                const float* bias, float* C, int64_t ldc, int64_t M, int K, int N, int accumulate, cudaStream_t st,
                const float* rowbias = nullptr, int64_t ld_rowbias = 0, const int64_t* seg = nullptr,
-               const float* alpha = nullptr, float* amax_out = nullptr);
+               const float* alpha = nullptr, float* amax_out = nullptr, float* stats_part = nullptr);
 bool wgrad_shape_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* dH, int64_t ldh);
 void wgrad_split(int64_t M, int K, int N, int* splits, int* kb_per_split);
 int64_t wgrad_workspace_bytes(int64_t M, int K, int N);
@@ -347,31 +347,39 @@ static int launch_sgemm(const float* P, int64_t ldp, const float* Q, int64_t ldq
 
 namespace gcs {
 
-// Inference form of one dense block: C = prelu((A . W + b) * scale + shift, alpha) in ONE tensor-core
-// GEMM - the moving-statistics BatchNorm is folded into the split weights (columns times scale) and the bias
-// (b * scale + shift), PReLU runs in the epilogue (alpha == NULL: none).  Needs the fp16 path (|max| of A known through
-// amax_sink().consume, reduction in one chain); *used = 0 otherwise and nothing was launched.  amax_out (optional):
-// cell that receives the |max| of C (zeroed here).
-int linear_fwd_bn_prelu(const float* A, int64_t lda, const float* W, const float* bias, const float* scale,
-                        const float* shift, const float* alpha, float* C, int64_t ldc, int64_t M, int K, int N,
-                        void* workspace, int64_t workspace_bytes, float* amax_out, cudaStream_t st, int* used) {
+// One dense block as ONE fp16 tensor-core GEMM with a fused epilogue.
+//  * inference (scale != NULL): C = prelu((A . W + b) * scale + shift, alpha) - the moving-statistics
+//    BatchNorm is folded into the split weights (columns times scale) and the bias (b * scale + shift), PReLU runs in the
+//    epilogue (alpha == NULL: none); amax_out (optional) receives the |max| of C (zeroed here).
+//  * training (scale == NULL, stats_part != NULL): C = A . W + b, and the epilogue leaves {sum, sum of squares} per
+//    32-row group and column in stats_part [ceil(M/32)][N][2] for the BatchNorm that follows (bn_stats_from_partials).
+// Needs the fp16 path (|max| of A known through amax_sink().consume, reduction in one chain); *used = 0 otherwise and
+// nothing was launched.
+int linear_fwd_fused(const float* A, int64_t lda, const float* W, const float* bias, const float* scale,
+                     const float* shift, const float* alpha, float* C, int64_t ldc, int64_t M, int K, int N,
+                     void* workspace, int64_t workspace_bytes, float* amax_out, float* stats_part, cudaStream_t st,
+                     int* used) {
   *used = 0;
   const float* a_amax = amax_sink().consume;
   const int64_t need = round_up(4LL * K * N, 256) + 256 + round_up(4LL * N, 256);
   if (g_gemm_mode == 1 || !tc::f16_mode() || !a_amax || !tc::f16_shape_ok(K) || K > tc::f16_max_chain() ||
-      !tc::shape_ok(M, K, N, A, lda, C, ldc, nullptr) || !workspace || !aligned16(workspace) || workspace_bytes < need ||
+      !tc::shape_ok(M, K, N, A, lda, C, ldc, bias) || !workspace || !aligned16(workspace) || workspace_bytes < need ||
       (alpha && !aligned16(alpha)))
     return GCS_OK;
   char* hi = static_cast<char*>(workspace);
   char* lo = hi + 2LL * K * N;
   float* cells = tc::f16_cells(workspace, K, N);
-  float* bias2 = cells + 64;
+  const float* b = bias;
   GCS_TRY(tc::f16_begin(cells, st));
   GCS_TRY(tc::absmax(W, N, K, N, cells, st, scale));
-  GCS_TRY(tc::fold_bias(bias, scale, shift, N, bias2, st));
+  if (scale) {
+    float* bias2 = cells + 64;
+    GCS_TRY(tc::fold_bias(bias, scale, shift, N, bias2, st));
+    b = bias2;
+  }
   GCS_TRY(tc::split_f16_strided(W, K, N, N, true, K, hi, lo, cells, st, scale));
   if (amax_out) GCS_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
-  GCS_TRY(tc::launch_f16(A, lda, hi, lo, cells, a_amax, bias2, C, ldc, M, K, N, 0, st, nullptr, 0, nullptr, alpha, amax_out));
+  GCS_TRY(tc::launch_f16(A, lda, hi, lo, cells, a_amax, b, C, ldc, M, K, N, 0, st, nullptr, 0, nullptr, alpha, amax_out, stats_part));
   *used = 1;
   return GCS_OK;
 }

@@ -274,7 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : k
     const float* __restrict__ bias, int64_t M, int K, int n_tiles, int num_tiles, int accumulate,
     const float* __restrict__ rowbias, int64_t ld_rowbias, const int64_t* __restrict__ seg,
     const float* __restrict__ a_amax, const float* __restrict__ b_scale_inv, const float* __restrict__ alpha,
-    float* __restrict__ amax_out) {
+    float* __restrict__ amax_out, float* __restrict__ stats_part) {
   constexpr int kPStages = kF16 ? kHStages : tc::kPStages;
   constexpr uint32_t P_STAGE_BYTES = kF16 ? H_STAGE_BYTES : tc::P_STAGE_BYTES;
   constexpr uint32_t A_BYTES = kF16 ? 2 * A_RAW_BYTES : A_RAW_BYTES;
@@ -508,6 +508,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : k
             else tma_store_2d(&map_c, sbuf, n0 + c0, crow);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // BatchNorm statistics of the layer's output without another pass over it: lane c sums column c of the staged
+        // box (its 32 rows; rows past M excluded) - {sum, sum of squares} per 32-row group and column, fp32, folded in
+        // fp64 by bn_stats_from_partials.  The swizzled box is read conflict-free (one 128 B row per step).
+        const int64_t grow = m0 + quarter * 32;
+        if (stats_part && grow < M) {
+          float ssum = 0.f, ssq = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            float hv;
+            const uint32_t src = sbuf + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + (lane & 3) * 4;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hv) : "r"(src));
+            if (grow + rr < M) {
+              ssum += hv;
+              ssq = fmaf(hv, hv, ssq);
+            }
+          }
+          reinterpret_cast<float2*>(stats_part)[(grow >> 5) * (static_cast<int64_t>(n_tiles) * BN) + n0 + c0 + lane] = make_float2(ssum, ssq);
         }
       } else {
   #pragma unroll 1
@@ -1233,7 +1251,7 @@ int launch(const float* A, int64_t lda, const float* Bt_hi, const float* Bt_lo, 
     const bool first = k0 == 0;
     linear_tc_pair_kernel<false><<<grid, kThreads, kPSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
                                                                       first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
-                                                                      seg, nullptr, nullptr, nullptr, nullptr);
+                                                                      seg, nullptr, nullptr, nullptr, nullptr, nullptr);
     GCS_CHECK_LAUNCH("linear_tc_pair_kernel");
   }
   return GCS_OK;
@@ -1288,9 +1306,10 @@ int split_f16_strided(const float* W, int rows, int cols, int64_t ldw, bool tran
 // Bt: fp16 split weights [N][K] (hi, lo), cells as left by split_f16_strided; a_amax: device |max| of A.
 int launch_f16(const float* A, int64_t lda, const void* Bt_hi, const void* Bt_lo, const float* cells, const float* a_amax,
                const float* bias, float* C, int64_t ldc, int64_t M, int K, int N, int accumulate, cudaStream_t st,
-               const float* rowbias, int64_t ld_rowbias, const int64_t* seg, const float* alpha, float* amax_out) {
-  if ((alpha || amax_out) && K > g_max_chain_k_f16)
-    return fail(GCS_ERR_UNSUPPORTED, "launch_f16: the PReLU / |max| epilogue needs the reduction in one chain");
+               const float* rowbias, int64_t ld_rowbias, const int64_t* seg, const float* alpha, float* amax_out,
+               float* stats_part) {
+  if ((alpha || amax_out || stats_part) && K > g_max_chain_k_f16)
+    return fail(GCS_ERR_UNSUPPORTED, "launch_f16: the PReLU / |max| / statistics epilogue needs the reduction in one chain");
   alignas(64) CUtensorMap ma, mh, ml, mc;
   GCS_TRY(make_map(&mc, C, M, N, ldc, 32, 32));
   static bool attr = false;
@@ -1314,7 +1333,7 @@ int launch_f16(const float* A, int64_t lda, const void* Bt_hi, const void* Bt_lo
     const bool first = k0 == 0;
     linear_tc_pair_kernel<true><<<grid, kHThreads, kHSmemBytes, st>>>(ma, mh, ml, mc, first ? bias : nullptr, M, kc, n_tiles, num_tiles,
                                                                      first ? accumulate : 1, first ? rowbias : nullptr, ld_rowbias,
-                                                                     seg, a_amax, cells + 1, alpha, amax_out);
+                                                                     seg, a_amax, cells + 1, alpha, amax_out, stats_part);
     GCS_CHECK_LAUNCH("linear_tc_pair_kernel<f16>");
   }
   return GCS_OK;

@@ -33,9 +33,12 @@ int dense_dx_concat(const float* dh, int64_t ld, const float* const* W, const in
                     int n_graphs, float* C, int64_t ldc, int64_t M, int accumulate, void* workspace,
                     int64_t workspace_bytes, cudaStream_t st);
 
-int linear_fwd_bn_prelu(const float* A, int64_t lda, const float* W, const float* bias, const float* scale,
-                        const float* shift, const float* alpha, float* C, int64_t ldc, int64_t M, int K, int N,
-                        void* workspace, int64_t workspace_bytes, float* amax_out, cudaStream_t st, int* used);
+int linear_fwd_fused(const float* A, int64_t lda, const float* W, const float* bias, const float* scale,
+                     const float* shift, const float* alpha, float* C, int64_t ldc, int64_t M, int K, int N,
+                     void* workspace, int64_t workspace_bytes, float* amax_out, float* stats_part, cudaStream_t st,
+                     int* used);
+int bn_stats_from_partials(const float* part, int64_t M, int C, float* mean, float* var, void* workspace,
+                           int64_t workspace_bytes, gcs_stream stream);
 namespace tc { int amax_merge(float* cell, const float* other, cudaStream_t st); }
 
 struct BlockDesc {
@@ -140,6 +143,7 @@ struct Plan {
   void* lw_ws = nullptr;
   int64_t lw_ws_bytes = 0;
   float* amax = nullptr;        // [0] running |max| of the node-level activations, [1] of the pre-BatchNorm gradients dh
+  float* stat_part = nullptr;   // [ceil(N/32)][H][2] {sum, sum of squares} per 32-row group, left by the GEMM epilogue
 };
 
 // Sets the thread's AmaxSink for the calls inside a scope (see common.cuh: feeds the fp16 tensor-core GEMMs).
@@ -162,6 +166,7 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
   Arena a(ws);
   p.amax = a.take<float>(64);
   const int64_t NH = N * p.H;
+  if (training) p.stat_part = a.take<float>(ceil_div(N > 0 ? N : 1, 32) * p.H * 2);
   p.cat = a.take<float>(NH * (p.L + 1));         // 'cat': one [N, H(L+1)] matrix; otherwise L+1 slabs [N, H]
   p.h.assign(p.P + p.L, nullptr);
   if (training) {
@@ -242,7 +247,8 @@ static int check_batch(const gcs_model_config& c, const gcs_batch* b, bool need_
 
 // BatchNorm statistics -> folded scale/shift for block bi over `rows` rows of h.
 static int block_norm(const gcs_model_config& c, const Plan& p, int bi, const float* params, float* state,
-                      const float* h, int64_t ldh, int64_t rows, bool training, gcs_stream st) {
+                      const float* h, int64_t ldh, int64_t rows, bool training, gcs_stream st,
+                      const float* stat_part = nullptr) {
   const BlockDesc& b = p.blocks[bi];
   float* mean = p.stat[bi];
   float* var = mean + b.m_out;
@@ -251,7 +257,8 @@ static int block_norm(const gcs_model_config& c, const Plan& p, int bi, const fl
   float* mm = state + b.stat_off;
   float* mv = mm + b.m_out;
   if (training) {
-    GCS_TIMED("bn_stats", gcs_bn_stats(h, ldh, rows, b.m_out, mean, var, p.bn_ws, p.bn_ws_bytes, st));
+    if (stat_part) GCS_TIMED("bn_stats", bn_stats_from_partials(stat_part, rows, b.m_out, mean, var, p.bn_ws, p.bn_ws_bytes, st));
+    else GCS_TIMED("bn_stats", gcs_bn_stats(h, ldh, rows, b.m_out, mean, var, p.bn_ws, p.bn_ws_bytes, st));
     GCS_TRY(gcs_bn_fold(mean, var, params + b.gamma(), params + b.beta(), c.bn_epsilon, c.bn_momentum, mm, mv,
                         scale, shift, b.m_out, st));
   } else {
@@ -288,14 +295,21 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
       // inference: moving-statistics BatchNorm folded into the GEMM, PReLU in its epilogue (one pass instead of three);
       // the |max| of the result goes through a scratch cell so that the GEMM does not raise the cell it reads
       GCS_TRY(block_norm(c, p, j, params, state, nullptr, H, N, false, st));
-      GCS_TIMED("linear_fwd", linear_fwd_bn_prelu(in, ld_in, params + b.kernel(), params + b.bias(), scale, scale + H,
-                                                  params + b.alpha(), out, ld_out, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes,
-                                                  p.amax + 2, as_stream(st), &fused));
+      GCS_TIMED("linear_fwd", linear_fwd_fused(in, ld_in, params + b.kernel(), params + b.bias(), scale, scale + H,
+                                               params + b.alpha(), out, ld_out, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes,
+                                               p.amax + 2, nullptr, as_stream(st), &fused));
       if (fused) GCS_TRY(tc::amax_merge(p.amax, p.amax + 2, as_stream(st)));
     }
     if (!fused) {
-      GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
-      GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st));
+      // training: the GEMM epilogue leaves the BatchNorm sums of its output (no separate pass over h) where it can
+      int with_stats = 0;
+      if (training)
+        GCS_TIMED("linear_fwd", linear_fwd_fused(in, ld_in, params + b.kernel(), params + b.bias(), nullptr, nullptr, nullptr,
+                                                 p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, nullptr, p.stat_part,
+                                                 as_stream(st), &with_stats));
+      if (!with_stats)
+        GCS_TIMED("linear_fwd", gcs_linear_fwd(in, ld_in, params + b.kernel(), params + b.bias(), p.h[j], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
+      GCS_TRY(block_norm(c, p, j, params, state, p.h[j], H, N, training, st, with_stats ? p.stat_part : nullptr));
       GCS_TIMED("bn_prelu_fwd", gcs_bn_prelu_fwd(p.h[j], H, scale, scale + H, params + b.alpha(), out, ld_out, N, H, st));
     }
     in = out;
@@ -312,9 +326,9 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     if (!training) {
       // inference: p.h[bi] receives prelu(bn(out . W + b)) straight from the GEMM; the aggregation is a plain gather
       GCS_TRY(block_norm(c, p, bi, params, state, nullptr, H, N, false, st));
-      GCS_TIMED("linear_fwd", linear_fwd_bn_prelu(cin, ld_emb, params + b.kernel(), params + b.bias(), scale, scale + H,
-                                                  params + b.alpha(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes,
-                                                  nullptr, as_stream(st), &fused));
+      GCS_TIMED("linear_fwd", linear_fwd_fused(cin, ld_emb, params + b.kernel(), params + b.bias(), scale, scale + H,
+                                               params + b.alpha(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes,
+                                               nullptr, nullptr, as_stream(st), &fused));
     }
     if (fused) {
       GCS_TIMED("spmm_fwd", gcs_spmm_aggregate(bt.rowptr, bt.colidx, nullptr, bt.rb4_blk_ptr, bt.rb4_ent, N, p.h[bi], H,
@@ -322,8 +336,14 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
                                                emb(k + 1), ld_emb, H, 0, st));
       continue;
     }
-    GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, ld_emb, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
-    GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st));
+    int with_stats = 0;
+    if (training)
+      GCS_TIMED("linear_fwd", linear_fwd_fused(cin, ld_emb, params + b.kernel(), params + b.bias(), nullptr, nullptr, nullptr,
+                                               p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, nullptr, p.stat_part,
+                                               as_stream(st), &with_stats));
+    if (!with_stats)
+      GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, ld_emb, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
+    GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st, with_stats ? p.stat_part : nullptr));
     // z_k is the leading block of out_{k+1} ('cat'), or out_{k+1} = z_k (+ out_k for 'sum') in the next slab
     GCS_TIMED("spmm_fwd", gcs_spmm_aggregate(bt.rowptr, bt.colidx, nullptr, bt.rb4_blk_ptr, bt.rb4_ent, N,
                                              p.h[bi], H, scale, scale + H, params + b.alpha(),
