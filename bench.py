@@ -251,7 +251,7 @@ def run_b200(args):
         t = ms / cnt / 1e3
         alg = 4.0 * n_nodes * HIDDEN * 2 + 4.0 * nnz + 4.0 * (n_nodes + 1)
         ach = alg / t / 1e9
-        roofline = {"kernel": "spmm_graph_kernel (K3, GeneralConv aggregation fwd, BN+PReLU fused on load)",
+        roofline = {"kernel": "spmm_rb4_kernel<true> (K3, GeneralConv aggregation fwd, BN+PReLU fused on load)",
                     "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": _ncu_traffic(),
                     "traffic_source": "profiles/r01_spmm_rb4_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
