@@ -70,6 +70,21 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        """Start of the timed region: the sampler itself is started earlier (before the warm-up steps), because
+        nvidia-smi's start-up (NVML initialisation) stalls kernel launches for tens of milliseconds."""
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def wait_ready(self, timeout=3.0):
+        """Block until nvidia-smi has delivered its first line (its initialisation is over)."""
+        t = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
 
     def start(self):
         try:
@@ -83,7 +98,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -95,7 +110,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [ln for t, ln in self.lines if (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1 + 0.03)]
+        if not lines:                                     # a timed region shorter than one sampling period
+            lines = [ln for t, ln in self.lines if self.t0 is None or t >= self.t0] or [ln for _, ln in self.lines[-1:]]
+        for ln in lines:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -205,13 +223,16 @@ def run_b200(args):
         stats["n"], stats["nnz"] = a.n_rows, a.nnz
         trainer.train_step((x, a, i), y)
 
-    for _ in range(W):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                   # before the warm-up: its start-up must not sit in the timed region
+        sampler.wait_ready()
+    for _ in range(W):
+        step()
     launches0 = lib.gcs_debug_launch_count()
+    sampler.mark_begin()
     ms_total = timed(step, K)
+    sampler.mark_end()
     launches = lib.gcs_debug_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / K
