@@ -44,3 +44,33 @@ def test_pair_graph_restatement_matches_the_reference():
         na = len(cas[a])
         for b1, b2 in GOLD[f"pair{k}_bridges"]:
             assert m[b1, na + b2] == 1 and m[na + b2, b1] == 1
+
+
+def test_vectorised_restatement_equals_the_literal_loop_on_random_chains():
+    """Property check with hypothesis: for random small chains (including coincident residues and coordinates that make
+    distances straddle the threshold) the vectorised float32 restatement equals the reference's literal double loop
+    bit for bit, the adjacency is symmetric with a full diagonal, and linking adds exactly the bridge edges."""
+    from hypothesis import given, settings, strategies as st
+
+    coords = st.lists(st.tuples(*[st.floats(-30, 30, width=32) for _ in range(3)]), min_size=1, max_size=14)
+
+    @settings(max_examples=40, deadline=None)
+    @given(coords, coords, st.integers(0, 2 ** 31 - 1))
+    def check(ca, cb, seed):
+        ca, cb = np.asarray(ca, np.float32), np.asarray(cb, np.float32)
+        d = contact_ref.distance_matrix(ca)
+        assert np.array_equal(d, contact_ref.distance_matrix_loop(ca))
+        adj_a, _ = contact_ref.proximity_matrix(ca, 10)
+        adj_b, _ = contact_ref.proximity_matrix(cb, 10)
+        assert np.array_equal(adj_a, adj_a.T) and np.all(np.diag(adj_a) == 1)
+        rng = np.random.default_rng(seed)
+        bridges = [(int(rng.integers(len(ca))), int(rng.integers(len(cb)))) for _ in range(int(rng.integers(0, 5)))]
+        m = contact_ref.pair_adjacency(adj_a, adj_b, bridges).toarray()
+        na = len(ca)
+        expect = np.zeros_like(m)
+        expect[:na, :na], expect[na:, na:] = adj_a, adj_b
+        for b1, b2 in bridges:
+            expect[b1, na + b2] = expect[na + b2, b1] = 1
+        assert np.array_equal(m, expect)
+
+    check()

@@ -229,6 +229,37 @@ def test_library_exports_every_declared_symbol():
     assert lib.gcs_model_workspace_bytes(c, 1000, 12000, 4, 1) > lib.gcs_model_workspace_bytes(c, 1000, 12000, 4, 0) > 0
 
 
+def test_ctypes_prototypes_match_the_header_signatures():
+    """Every declaration of include/gcnstring_b200.h against its entry in _lib.PROTOTYPES: same number of parameters,
+    and per parameter the same class (pointer / 32-bit / 64-bit integer / float / double) - a drifted binding would
+    corrupt the stack silently."""
+    import ctypes
+    from gcn_string_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "gcnstring_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = re.findall(r"\b(?:int|int32_t|int64_t|const char\s*\*|void)\s+(gcs_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) >= 30
+
+    def klass_c(param):
+        param = " ".join(param.split())
+        if param in ("void", ""):
+            return None
+        if "*" in param or param.startswith("gcs_stream") or param.startswith("gcs_allreduce_fn"):
+            return "ptr"
+        ty = param.rsplit(" ", 1)[0].replace("const ", "")
+        return {"int32_t": "i32", "int": "i32", "int64_t": "i64", "float": "f32", "double": "f64"}[ty]
+
+    def klass_py(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_int32: "i32", ctypes.c_int64: "i64", ctypes.c_float: "f32", ctypes.c_double: "f64"}[t]
+
+    for name, params in decls:
+        want = [k for k in (klass_c(q) for q in params.split(",")) if k is not None]
+        got = [klass_py(t) for t in _lib.PROTOTYPES[name][1]]
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
+
+
 def test_product_path_does_not_import_oracle():
     pkg = os.path.join(ROOT, "gcn-string_b200")
     for dirpath, _, files in os.walk(pkg):
