@@ -187,9 +187,9 @@ def run_b200(args):
     np.random.seed(1234 + rank)
     sched = g.optimizers.schedules.PiecewiseConstantDecay([0, 1], [0.02, 0.002, 0.0002])   # gcn.py:321-325
 
-    def make(device_resident, shuffle):
+    def make(device_resident, shuffle, **store_kw):
         loader = g.DisjointLoader(ds, batch_size=B, epochs=None, shuffle=shuffle, symmetric=True,
-                                  device_resident=device_resident)      # each rank owns its pool: shards are per-rank here
+                                  device_resident=device_resident, **store_kw)   # each rank owns its pool: shards are per-rank here
         model = g.GeneralGNN(CLASSES, activation="softmax", hidden=HIDDEN, message_passing=LAYERS, seed=0)
         model.build(N_FEAT)
         trainer = DataParallelTrainer(model, g.optimizers.SGD(learning_rate=sched), sync_bn=args.sync_bn)
@@ -299,7 +299,7 @@ def run_b200(args):
     torch.cuda.empty_cache()
 
     # ------------------------------------------------ host-resident arm (`e2e`)
-    loader_h, model_h, trainer_h = make(False, False)
+    loader_h, model_h, trainer_h = (make(False, True, device_gather=True) if args.e2e_shuffle else make(False, False))
     io = {"k": 0}
     host_loss = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
     copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -348,7 +348,10 @@ def run_b200(args):
                          "every step", "bn": ("synchronised BatchNorm statistics (16 extra fp64 all-reduces of <= 3H+1 values per step)"
                           if args.sync_bn and world > 1 else "replica-local BatchNorm statistics")},
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(io["h2d"]),
-                "d2h_bytes_per_step": 8, "note": "dataset in pinned host memory, consecutive batches; per step: H2D of the batch's "
+                "d2h_bytes_per_step": 8, "note": ("dataset in pinned host memory, reshuffled batches; per step: a device kernel gathers "
+                         "the batch's packed graphs out of the pinned arrays (H2D), device batching, train step, D2H of {loss, acc} "
+                         "into a pinned buffer that the host reads one step later") if args.e2e_shuffle else
+                "dataset in pinned host memory, consecutive batches; per step: H2D of the batch's "
                 "packed graphs (cudaMemcpyAsync from the pinned arrays), device batching, train step, D2H of {loss, acc} into a "
                 "pinned buffer that the host reads one step later"},
         "gpu_launches": int(launches),
@@ -395,6 +398,8 @@ def main():
     ap.add_argument("--batch-graphs", type=int, default=B_GRAPHS)
     ap.add_argument("--pool-batches", type=int, default=4, help="synthetic pool size in batches per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-shuffle", action="store_true", help="e2e arm with reshuffled batches: the selected graphs are "
+                    "gathered out of pinned host memory by a device kernel (gcs_gather_graphs) instead of sliced copies")
     ap.add_argument("--sync-bn", action="store_true", help="all-reduce the BatchNorm statistics too (a G-GPU step then "
                     "equals one step on the union batch); off by default: the gradient all-reduce is the only collective")
     args = ap.parse_args()

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "gcs_device_sm_count": (c_int32, []),
     "gcs_set_allreduce_hook": (c_int32, [P, P, I32]),
     "gcs_batch_disjoint": (c_int32, [P, P, P, P, P, I32, I32, P, I32, I64, I64, P, P, P, P, P, P, P, P, P, P]),
+    "gcs_gather_graphs": (c_int32, [P, I32, P, P, P, P, P, I32, I32, P, P, P, P, P, P, P]),
     "gcs_coo_to_csr": (c_int32, [P, I64, I64, P, P, P, P]),
     "gcs_segment_ptr": (c_int32, [P, I64, I32, P, P, P]),
     "gcs_csr_is_symmetric": (c_int32, [P, P, I64, P, P]),

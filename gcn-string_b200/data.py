@@ -246,8 +246,12 @@ class HostGraphStore:
     (cfg3 step, 94 MB per batch): the kernel's row-granular reads reach only 4-6 GB/s over the host link, 18.8-27 ms
     per step against 17.6 ms for the sliced upload, so it is an option for shuffled epochs, not the default."""
 
-    def __init__(self, packed: PackedGraphs, symmetric: Optional[bool] = None, zero_copy: bool = False):
+    def __init__(self, packed: PackedGraphs, symmetric: Optional[bool] = None, zero_copy: bool = False,
+                 device_gather: bool = False):
         self.zero_copy = bool(zero_copy)
+        # device_gather=True: a non-consecutive (shuffled) batch is gathered by gcs_gather_graphs - a kernel that copies
+        # each selected graph's slices out of the pinned arrays in coalesced runs - instead of a Python loop on the host
+        self.device_gather = bool(device_gather)
         torch = _lib.require_cuda()
         _lib.load()
         self.n_graphs = packed.n_graphs
@@ -288,6 +292,10 @@ class HostGraphStore:
             parts = (self.node_off[g0:g1 + 1], self.rowptr[n0:n1 + 1], self.col[e0:e1], self.x[n0:n1],
                      self.y[g0:g1] if self.y is not None else None)
             ids_local = torch.arange(g0, g1, dtype=torch.int64)
+        elif self.device_gather:
+            parts = None
+            g0 = n0 = e0 = 0
+            ids_local = torch.arange(0, b, dtype=torch.int64)
         else:
             parts = self._gather(ids)
             g0 = n0 = e0 = 0
@@ -301,6 +309,24 @@ class HostGraphStore:
             ids_dev = ids_local.pin_memory().cuda(non_blocking=True)
             # bytes the kernel pulls over the host link: per graph its node offsets, row pointers, columns, features, label
             self.h2d_bytes_last = 16 * b + 8 * (n + b) + 4 * nnz + 4 * self.n_feat * n + 4 * self.n_classes * b + 8 * b
+        elif parts is None:
+            # the selected graphs' offsets in the mini-dataset (host knows the sizes), then one gather kernel
+            off = np.zeros((3, b + 1), dtype=np.int64)
+            np.cumsum(self.h_n_nodes[ids], out=off[0, 1:])
+            np.cumsum(self.h_n_edges[ids], out=off[1, 1:])
+            off[2, :b] = ids
+            off_dev = torch.from_numpy(off).pin_memory().cuda(non_blocking=True)
+            d_node_off = off_dev[0]
+            d_rowptr = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+            d_col = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
+            d_x = torch.empty(max(n, 1), self.n_feat, dtype=torch.float32, device="cuda")
+            d_y = torch.empty(b, self.n_classes, dtype=torch.float32, device="cuda") if self.y is not None else None
+            check(lib.gcs_gather_graphs(ptr(off_dev[2]), b, ptr(self.node_off), ptr(self.rowptr), ptr(self.col), ptr(self.x),
+                                        ptr(self.y), self.n_feat, self.n_classes, ptr(off_dev[0]), ptr(off_dev[1]),
+                                        ptr(d_rowptr), ptr(d_col), ptr(d_x), ptr(d_y), stream_ptr()), "gcs_gather_graphs")
+            dev = [d_node_off, d_rowptr, d_col, d_x, d_y]
+            ids_dev = ids_local.pin_memory().cuda(non_blocking=True)
+            self.h2d_bytes_last = 16 * b + 8 * (n + b) + 4 * nnz + 4 * self.n_feat * n + 4 * self.n_classes * b + 24 * (b + 1)
         else:
             dev = [t.cuda(non_blocking=True) if t is not None else None for t in parts]
             ids_dev = ids_local.pin_memory().cuda(non_blocking=True)
@@ -375,7 +401,8 @@ class DisjointLoader:
     """
 
     def __init__(self, dataset, node_level=False, batch_size=1, epochs=None, shuffle=True, rank=0, world_size=1,
-                 want_coo=False, symmetric=None, device_resident=True, prefetch=None, balance=None, zero_copy=False):
+                 want_coo=False, symmetric=None, device_resident=True, prefetch=None, balance=None, zero_copy=False,
+                 device_gather=False):
         if node_level:
             raise NotImplementedError("node_level=True labels are not built (reference uses graph labels)")
         packed = dataset if isinstance(dataset, PackedGraphs) else pack_graphs(list(dataset))
@@ -386,7 +413,7 @@ class DisjointLoader:
         self.dataset = dataset
         # device_resident=False keeps the dataset in pinned host memory and uploads per batch
         self.store = (DeviceGraphStore(packed, symmetric=symmetric) if device_resident
-                      else HostGraphStore(packed, symmetric=symmetric, zero_copy=zero_copy))
+                      else HostGraphStore(packed, symmetric=symmetric, zero_copy=zero_copy, device_gather=device_gather))
         self.node_level = node_level
         self.batch_size = int(batch_size)
         self.epochs = epochs

@@ -76,6 +76,16 @@ int gcs_batch_disjoint(const int64_t* ds_node_off, const int64_t* ds_rowptr, con
                        float* x, int64_t* seg_ids, float* y, int64_t* coo_indices,
                        int32_t* status_dev, gcs_stream stream);
 
+/* Whole-graph gather for a streaming loader: copies the graphs graph_ids[0..n_graphs) of a packed dataset - typically
+ * resident in PINNED HOST memory, read by the kernel over the host link in coalesced runs - into a packed mini-dataset
+ * on the device (node_off = dst_node_off, rebased row pointers, graph-local columns, features, labels) that
+ * gcs_batch_disjoint then batches with graph ids 0..n_graphs-1.  dst_node_off / dst_edge_off [n_graphs + 1] (device):
+ * exclusive prefix sums of the selected graphs' node / entry counts, which the host knows.  src_y / dst_y may be NULL. */
+int gcs_gather_graphs(const int64_t* graph_ids, int32_t n_graphs, const int64_t* src_node_off,
+                      const int64_t* src_rowptr, const int32_t* src_col, const float* src_x, const float* src_y,
+                      int32_t n_feat, int32_t n_classes, const int64_t* dst_node_off, const int64_t* dst_edge_off,
+                      int64_t* dst_rowptr, int32_t* dst_col, float* dst_x, float* dst_y, gcs_stream stream);
+
 /* Row-major-sorted COO (what tf.sparse.reorder returns; Spektral's
  * sp_matrix_to_sp_tensor) -> int32 CSR.  *status_dev != 0 if unsorted/out of range. */
 int gcs_coo_to_csr(const int64_t* coo_indices, int64_t nnz, int64_t n_rows, int32_t* rowptr,

@@ -392,7 +392,8 @@ def test_host_store_zero_copy_and_staged_upload_equal_the_resident_store():
     store, shuffled and with a short last batch; the byte counts they report are those of the batch's graphs."""
     ds = synthetic.make_dataset(11, seed=5, n_mean=50, deg=8, n_feat=7)
     runs = []
-    for kw in (dict(device_resident=True), dict(device_resident=False, zero_copy=True), dict(device_resident=False)):
+    for kw in (dict(device_resident=True), dict(device_resident=False, zero_copy=True), dict(device_resident=False),
+               dict(device_resident=False, device_gather=True)):
         np.random.seed(77)
         ld = g.DisjointLoader(ds, batch_size=4, epochs=2, shuffle=True, want_coo=True, prefetch=False, **kw)
         out = []
@@ -400,7 +401,7 @@ def test_host_store_zero_copy_and_staged_upload_equal_the_resident_store():
             out.append([host(t) for t in (x, a.indices, a.rowptr, a.colidx, a.graph_ptr, i, y)])
             if not kw["device_resident"]:
                 b, n, nnz = y.shape[0], x.shape[0], a.nnz
-                assert 4 * nnz + 4 * 7 * n <= ld.store.h2d_bytes_last <= 4 * nnz + 4 * 7 * n + 16 * n + 64 * b + 64
+                assert 4 * nnz + 4 * 7 * n <= ld.store.h2d_bytes_last <= 4 * nnz + 4 * 7 * n + 16 * n + 96 * b + 96
         runs.append(out)
     assert len(runs[0]) == 6
     np.random.seed(77)                                        # and with the next batch in flight on a side stream
