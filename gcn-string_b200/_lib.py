@@ -26,10 +26,11 @@ class ModelConfig(Structure):
 
 
 class Batch(Structure):
-    _fields_ = [("n_nodes", c_int64), ("nnz", c_int64), ("n_graphs", c_int32), ("reserved", c_int32),
+    _fields_ = [("n_nodes", c_int64), ("nnz", c_int64), ("n_graphs", c_int32), ("rb_height", c_int32),
                 ("rowptr", c_void_p), ("colidx", c_void_p), ("rowptr_t", c_void_p), ("colidx_t", c_void_p),
                 ("graph_ptr", c_void_p), ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p),
-                ("seg_ids", c_void_p), ("rb4_blk_ptr", c_void_p), ("rb4_ent", c_void_p), ("rb4_blk_ptr_t", c_void_p), ("rb4_ent_t", c_void_p)]
+                ("seg_ids", c_void_p), ("rb4_blk_ptr", c_void_p), ("rb4_ent", c_void_p), ("rb4_blk_ptr_t", c_void_p), ("rb4_ent_t", c_void_p),
+                ("max_graph_nodes", c_int32), ("reserved", c_int32)]
 
 
 P = c_void_p
@@ -58,6 +59,10 @@ PROTOTYPES = {
     "gcs_bn_fold": (c_int32, [P, P, P, P, F32, F32, P, P, P, P, I32, P]),
     "gcs_bn_prelu_fwd": (c_int32, [P, I64, P, P, P, P, I64, I64, I32, P]),
     "gcs_bn_prelu_bwd": (c_int32, [P, I64, P, I64, P, P, P, P, P, F32, P, I64, P, P, P, P, I64, I32, P, I64, P]),
+    "gcs_spmm_rb_workspace_bytes": (c_int64, [I64, I32]),
+    "gcs_spmm_build_rb": (c_int32, [P, P, I64, I64, I32, P, P, P, I64, P]),
+    "gcs_spmm_slab_stage_bytes": (c_int64, []),
+    "gcs_spmm_sum_graphs": (c_int32, [P, I32, I32, P, P, P, P, I32, I64, P, I64, P, P, P, P, I64, P, I64, I32, P]),
     "gcs_spmm_rb4_workspace_bytes": (c_int64, [I64]),
     "gcs_spmm_build_rb4": (c_int32, [P, P, I64, I64, P, P, P, I64, P]),
     "gcs_spmm_sum": (c_int32, [P, P, P, P, I64, P, I64, P, P, P, P, I64, I32, P]),
@@ -100,7 +105,7 @@ def load() -> ctypes.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  gcn_string_b200 has no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(os.environ.get("GCS_LIB_PATH", LIB_PATH))     # GCS_LIB_PATH: a kernel-variant build (scripts only)
     for table in (PROTOTYPES, _DEBUG):
         for name, (res, args) in table.items():
             fn = getattr(lib, name)

@@ -245,6 +245,17 @@ static int check_batch(const gcs_model_config& c, const gcs_batch* b, bool need_
   return GCS_OK;
 }
 
+// Y = pattern(A) . f(X) (+ residual) for the batch: per-graph shared-memory slabs when the batch says how long its graphs
+// are (gcs_spmm_sum_graphs), the global-memory kernels otherwise.  transposed selects pattern(A)^T (the backward).
+static int aggregate(const gcs_batch& bt, bool transposed, const float* X, int64_t ldx, const float* scale, const float* shift,
+                     const float* alpha, const float* residual, int64_t ldr, float* Y, int64_t ldy, int H, gcs_stream st) {
+  const int height = bt.rb_height ? bt.rb_height : 4;
+  return gcs_spmm_sum_graphs(bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, transposed ? bt.rowptr_t : bt.rowptr,
+                             transposed ? bt.colidx_t : bt.colidx, transposed ? bt.rb4_blk_ptr_t : bt.rb4_blk_ptr,
+                             transposed ? bt.rb4_ent_t : bt.rb4_ent, height, bt.n_nodes, X, ldx, scale, shift, alpha, residual,
+                             ldr, Y, ldy, H, st);
+}
+
 // BatchNorm statistics -> folded scale/shift for block bi over `rows` rows of h.
 static int block_norm(const gcs_model_config& c, const Plan& p, int bi, const float* params, float* state,
                       const float* h, int64_t ldh, int64_t rows, bool training, gcs_stream st,
@@ -331,9 +342,8 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
                                                nullptr, nullptr, as_stream(st), &fused));
     }
     if (fused) {
-      GCS_TIMED("spmm_fwd", gcs_spmm_aggregate(bt.rowptr, bt.colidx, nullptr, bt.rb4_blk_ptr, bt.rb4_ent, N, p.h[bi], H,
-                                               nullptr, nullptr, nullptr, c.connectivity == 2 ? emb(k) : nullptr, H,
-                                               emb(k + 1), ld_emb, H, 0, st));
+      GCS_TIMED("spmm_fwd", aggregate(bt, false, p.h[bi], H, nullptr, nullptr, nullptr, c.connectivity == 2 ? emb(k) : nullptr, H,
+                                      emb(k + 1), ld_emb, H, st));
       continue;
     }
     int with_stats = 0;
@@ -345,9 +355,8 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
       GCS_TIMED("linear_fwd", gcs_linear_fwd(cin, ld_emb, params + b.kernel(), params + b.bias(), p.h[bi], H, N, b.k_in, H, p.lin_ws, p.lin_ws_bytes, st));
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st, with_stats ? p.stat_part : nullptr));
     // z_k is the leading block of out_{k+1} ('cat'), or out_{k+1} = z_k (+ out_k for 'sum') in the next slab
-    GCS_TIMED("spmm_fwd", gcs_spmm_aggregate(bt.rowptr, bt.colidx, nullptr, bt.rb4_blk_ptr, bt.rb4_ent, N,
-                                             p.h[bi], H, scale, scale + H, params + b.alpha(),
-                                             c.connectivity == 2 ? emb(k) : nullptr, H, emb(k + 1), ld_emb, H, 0, st));
+    GCS_TIMED("spmm_fwd", aggregate(bt, false, p.h[bi], H, scale, scale + H, params + b.alpha(),
+                                    c.connectivity == 2 ? emb(k) : nullptr, H, emb(k + 1), ld_emb, H, st));
   }
   // global sum pool
   amax_sink() = AmaxSink();                                 // pooled rows and the post-MLP: tf32 kernels / CUDA cores
@@ -470,8 +479,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
       dz = blk;
       lddz = Wc;
     }
-    GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb4_blk_ptr_t, bt.rb4_ent_t, N, dz, lddz, nullptr, nullptr,
-                                       nullptr, p.tmp_a, H, H, st));
+    GCS_TIMED("spmm_bwd", aggregate(bt, true, dz, lddz, nullptr, nullptr, nullptr, nullptr, 0, p.tmp_a, H, H, st));
     GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N, p.cat + static_cast<int64_t>(L - k) * H, Wc,
                            p.dhcat + static_cast<int64_t>(k) * H, ldd, nullptr, 0, 0, st));
   }
@@ -491,8 +499,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
       g = p.tmp_c;
     }
     for (int k = L - 1; k >= 0; --k) {
-      GCS_TIMED("spmm_bwd", gcs_spmm_sum(bt.rowptr_t, bt.colidx_t, bt.rb4_blk_ptr_t, bt.rb4_ent_t, N, g, H, nullptr, nullptr,
-                                         nullptr, p.tmp_a, H, H, st));
+      GCS_TIMED("spmm_bwd", aggregate(bt, true, g, H, nullptr, nullptr, nullptr, nullptr, 0, p.tmp_a, H, H, st));
       GCS_TRY(block_backward(c, p, P + k, params, grads, p.tmp_a, H, p.h[P + k], H, N, emb(k), ld_emb, p.dhcat, H, g, H,
                              c.connectivity == 2 ? 1 : 0, st));
     }

@@ -35,31 +35,31 @@ namespace gcs {
 //   2 rows: union 1.5x smaller                                                          399 / 272 us
 constexpr int kRB = 4;
 
-// kRB-way merge of the sorted neighbour lists of one row block; kFill = false counts the union size.
-template <bool kFill>
-__global__ void __launch_bounds__(128) rb4_build_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+// RB-way merge of the sorted neighbour lists of one row block; kFill = false counts the union size.
+template <int RB, bool kFill>
+__global__ void __launch_bounds__(128) rb_build_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                                         int n_rows, int n_blocks, const int32_t* __restrict__ blk_ptr,
                                                         int32_t* __restrict__ count, uint32_t* __restrict__ ent) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
-  int p[kRB], e[kRB], cur[kRB];
+  int p[RB], e[RB], cur[RB];
 #pragma unroll
-  for (int r = 0; r < kRB; ++r) {
-    const int row = b * kRB + r;
+  for (int r = 0; r < RB; ++r) {
+    const int row = b * RB + r;
     p[r] = row < n_rows ? __ldg(rowptr + row) : 0;
     e[r] = row < n_rows ? __ldg(rowptr + row + 1) : 0;
     cur[r] = p[r] < e[r] ? __ldg(colidx + p[r]) : INT32_MAX;
   }
-  int n = 0;
+  int n = 0, last = 0;
   uint32_t* out = kFill ? ent + __ldg(blk_ptr + b) : nullptr;
   while (true) {
     int cmin = cur[0];
 #pragma unroll
-    for (int r = 1; r < kRB; ++r) cmin = min(cmin, cur[r]);
+    for (int r = 1; r < RB; ++r) cmin = min(cmin, cur[r]);
     if (cmin == INT32_MAX) break;
     uint32_t mask = 0;
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) {
+    for (int r = 0; r < RB; ++r) {
       if (cur[r] == cmin) {
         mask |= 1u << r;
         ++p[r];
@@ -68,8 +68,16 @@ __global__ void __launch_bounds__(128) rb4_build_kernel(const int32_t* __restric
     }
     if (kFill) out[n] = (static_cast<uint32_t>(cmin) << 8) | mask;
     ++n;
+    last = cmin;
   }
-  if (!kFill) count[b] = n;
+  // pad to a multiple of 4 entries with no-ops (mask 0, a column of the block): every block then starts on a 16-byte
+  // boundary and the kernels read four entry words per load
+  const int padded = (n + 3) & ~3;
+  if (kFill) {
+    for (; n < padded; ++n) out[n] = static_cast<uint32_t>(last) << 8;
+  } else {
+    count[b] = padded;
+  }
 }
 
 // One row block per `lanes` threads (lanes = H/4, each lane owns 4 columns); a CTA walks a contiguous
@@ -286,12 +294,13 @@ int launch_rb4(const SpmmArgs& a) {
   return GCS_OK;
 }
 
-int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 whenever supplied
-
+int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 global-memory kernel whenever supplied (both: never the slab kernel)
 }  // namespace
 
 // Test / sweep hook (not part of the drop-in surface).
 extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
+namespace gcs { int spmm_mode() { return g_spmm_mode; } }
+namespace gcs { void slab_set_param(int id, int value); }
 namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); void set_wgrad_pair(int v); void set_f16_mode(int v); void set_max_chain_k_f16(int k); void set_wgrad_f16(int v); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
@@ -302,33 +311,47 @@ extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 7) gcs::tc::set_f16_mode(value);             // 0 tf32 only, 1 fp16 inside the fused model, 2 fp16 everywhere
   if (id == 8) gcs::tc::set_max_chain_k_f16(value);
   if (id == 9) gcs::tc::set_wgrad_f16(value);                // 0 = weight gradient on the tf32 split only
+  if (id == 10 || id == 11 || id == 12) gcs::slab_set_param(id, value);   // spmm_slab.cu: stages / stage bytes / grid
 }
 
-extern "C" int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows) {
-  return round_up((ceil_div(n_rows > 0 ? n_rows : 1, kRB) + 1) * static_cast<int64_t>(sizeof(int32_t)), 256);
+extern "C" int64_t gcs_spmm_rb_workspace_bytes(int64_t n_rows, int32_t rb_height) {
+  if (rb_height != 2 && rb_height != 4) return -1;
+  return round_up((ceil_div(n_rows > 0 ? n_rows : 1, rb_height) + 1) * static_cast<int64_t>(sizeof(int32_t)), 256);
 }
+extern "C" int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows) { return gcs_spmm_rb_workspace_bytes(n_rows, 4); }
 
-extern "C" int gcs_spmm_build_rb4(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
-                                  int32_t* blk_ptr, uint32_t* ent, void* workspace, int64_t workspace_bytes,
-                                  gcs_stream stream) {
-  GCS_CHECK_ARG(rowptr && blk_ptr && workspace && n_rows >= 0 && nnz >= 0, "gcs_spmm_build_rb4: bad argument");
-  GCS_CHECK_ARG(nnz == 0 || (colidx && ent), "gcs_spmm_build_rb4: null column / entry array");
-  GCS_CHECK_ARG(n_rows < (1 << 24), "gcs_spmm_build_rb4: RB4 packs the column index in 24 bits (n_rows < 16 777 216)");
-  if (workspace_bytes < gcs_spmm_rb4_workspace_bytes(n_rows))
-    return fail(GCS_ERR_WORKSPACE, "gcs_spmm_build_rb4: workspace too small");
+extern "C" int gcs_spmm_build_rb(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz, int32_t rb_height,
+                                 int32_t* blk_ptr, uint32_t* ent, void* workspace, int64_t workspace_bytes,
+                                 gcs_stream stream) {
+  GCS_CHECK_ARG(rb_height == 2 || rb_height == 4, "gcs_spmm_build_rb: block height must be 2 or 4");
+  GCS_CHECK_ARG(rowptr && blk_ptr && workspace && n_rows >= 0 && nnz >= 0, "gcs_spmm_build_rb: bad argument");
+  GCS_CHECK_ARG(nnz == 0 || (colidx && ent), "gcs_spmm_build_rb: null column / entry array");
+  GCS_CHECK_ARG(n_rows < (1 << 24), "gcs_spmm_build_rb: the format packs the column index in 24 bits (n_rows < 16 777 216)");
+  if (workspace_bytes < gcs_spmm_rb_workspace_bytes(n_rows, rb_height))
+    return fail(GCS_ERR_WORKSPACE, "gcs_spmm_build_rb: workspace too small");
   cudaStream_t st = as_stream(stream);
-  const int nb = static_cast<int>(ceil_div(n_rows, kRB));
+  const int nb = static_cast<int>(ceil_div(n_rows, rb_height));
   int32_t* cnt = static_cast<int32_t*>(workspace);
   if (nb == 0) {
     GCS_CUDA(cudaMemsetAsync(blk_ptr, 0, sizeof(int32_t), st));
     return GCS_OK;
   }
-  rb4_build_kernel<false><<<static_cast<unsigned>(ceil_div(nb, 128)), 128, 0, st>>>(rowptr, colidx, static_cast<int>(n_rows), nb, nullptr, cnt, nullptr);
-  GCS_CHECK_LAUNCH("rb4_build_kernel<count>");
+  const unsigned grid = static_cast<unsigned>(ceil_div(nb, 128));
+  const int n = static_cast<int>(n_rows);
+  if (rb_height == 2) rb_build_kernel<2, false><<<grid, 128, 0, st>>>(rowptr, colidx, n, nb, nullptr, cnt, nullptr);
+  else rb_build_kernel<4, false><<<grid, 128, 0, st>>>(rowptr, colidx, n, nb, nullptr, cnt, nullptr);
+  GCS_CHECK_LAUNCH("rb_build_kernel<count>");
   GCS_TRY(exclusive_scan_i32(cnt, nb, blk_ptr, st));
-  rb4_build_kernel<true><<<static_cast<unsigned>(ceil_div(nb, 128)), 128, 0, st>>>(rowptr, colidx, static_cast<int>(n_rows), nb, blk_ptr, nullptr, ent);
-  GCS_CHECK_LAUNCH("rb4_build_kernel<fill>");
+  if (rb_height == 2) rb_build_kernel<2, true><<<grid, 128, 0, st>>>(rowptr, colidx, n, nb, blk_ptr, nullptr, ent);
+  else rb_build_kernel<4, true><<<grid, 128, 0, st>>>(rowptr, colidx, n, nb, blk_ptr, nullptr, ent);
+  GCS_CHECK_LAUNCH("rb_build_kernel<fill>");
   return GCS_OK;
+}
+
+extern "C" int gcs_spmm_build_rb4(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
+                                  int32_t* blk_ptr, uint32_t* ent, void* workspace, int64_t workspace_bytes,
+                                  gcs_stream stream) {
+  return gcs_spmm_build_rb(rowptr, colidx, n_rows, nnz, 4, blk_ptr, ent, workspace, workspace_bytes, stream);
 }
 
 extern "C" int gcs_spmm_aggregate(const int32_t* rowptr, const int32_t* colidx, const float* values,

@@ -1,0 +1,600 @@
+// K3 / K7 for disjoint batches — Y = pattern(A) . f(X) with every graph staged in shared memory.
+//
+// A disjoint batch (spektral.data.DisjointLoader, src/scripts/gcn.py:316-317) is block-diagonal: every neighbour of a
+// node lies in the node's own graph.  One work item = (graph, 32 feature columns): that slice of
+// the graph's rows of X fits a shared-memory slab, so
+//   * every element of X leaves HBM exactly once, in 128-byte runs, by the TMA unit (2-D tensor copies of 32 rows);
+//   * the BatchNorm + PReLU prologue of GeneralConv (transform -> BN -> PReLU -> aggregate) is applied ONCE per
+//     element, in place, instead of once per gathered neighbour;
+//   * all gathers of the graph are 128-bit shared-memory loads: no L2 / DRAM latency inside the gather chain.
+// The kernel is persistent (one CTA per SM, 1024 threads) and warp-specialised, with a ring of 2-3 slabs:
+//   warp 0         producer: walks this CTA's work items, waits for a free slab, posts the item's descriptor and issues
+//                  the bulk copies (X slice, the graph's row-block entries) that complete on the slab's `landed` mbarrier;
+//   warps 1-4      prologue: wait `landed`, rewrite the entry words into ready-made shared-memory addresses, apply
+//                  f(x) = prelu(x*scale + shift, alpha) in place, arrive on `ready`;
+//   warps 5-31     gather: wait `ready`, take row blocks from a shared counter (4 blocks per warp at a time), sum each
+//                  block's neighbours out of the slab, store the rows of Y, arrive on `empty`.
+// so the HBM-bound staging of item i+1/i+2 overlaps the shared-memory-bound gather of item i and no warp ever waits
+// at a CTA-wide barrier.  Row blocks use the RB format of spmm.cu (height 2 or 4, blocks padded to 4 entries): a
+// neighbour row is read once per block, each lane owns 4 columns and adds with packed fp32x2 instructions; per output
+// row the summation order is ascending column, bit-identical to the CSR row kernel.  Row blocks are aligned to batch
+// rows, so the first / last block of a graph may straddle its neighbour: entries outside the graph's column range
+// become no-ops when the prologue warps rewrite them.  Graphs too long for a 32-column slab are walked in passes of
+// 16 / 8 / 4 columns; a graph whose entries do not fit even then is gathered straight from global memory by the same
+// warps (slow, correct).
+#include <cuda.h>
+
+#include "common.cuh"
+
+#ifndef GCS_SLAB_ADD_MODE
+#define GCS_SLAB_ADD_MODE 1   // 1 = FADD2 + 2 FADD per float4, 2 = 2 FADD2
+#endif
+
+namespace gcs {
+int spmm_mode();   // spmm.cu: gcs_debug_set_spmm_mode
+
+namespace slab {
+
+constexpr int kCols = 32;            // feature columns per work item
+constexpr int kThreads = 1024;
+constexpr int kXformWarps = 4;
+constexpr int kGatherWarps = 27;
+constexpr int kMaxStages = 3;
+constexpr int kHeaderBytes = 1024;
+constexpr int kBoxRows = 32;         // rows per TMA box: a graph's slab holds its row count rounded up to this
+constexpr uint32_t kAddrMask = 0x00FFFFF0u;
+
+struct Meta {
+  int mode;        // 0 = slab, 1 = direct (global-memory gather), -1 = stop
+  int off, n;      // the graph's first row and row count
+  int n_up;        // n rounded up to kBoxRows: rows the slab holds (the tail belongs to the next graph / is zero fill)
+  int lq;          // log2(lanes per row block) of this pass: cw = 4 << lq columns
+  int col0;        // first feature column of the pass
+  int b_first, nb; // the graph's row blocks
+  int e0;          // index of the graph's first entry in the global entry array
+  int ent_words;
+  int pad[2];
+};
+struct Maps { CUtensorMap m[4]; };   // X as a 2-D tensor, boxes of kBoxRows rows x (4 << k) columns, k = 0..3
+
+struct Header {
+  unsigned long long landed[kMaxStages], ready[kMaxStages], empty[kMaxStages];
+  Meta meta[kMaxStages];
+  int counter[kMaxStages];
+};
+static_assert(sizeof(Header) <= kHeaderBytes, "header too large");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA bulk copy global -> shared (16-byte aligned, size a multiple of 16), completing on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// acc += v: one packed fp32x2 add for (x, y) and two scalar adds for (z, w).  On sm_100 FADD2 issues once but runs on
+// the fma-heavy pipe only (4 cycles per warp), scalar FADD can also take the fma-lite pipe: splitting the float4 add
+// between them keeps both fp32 pipes busy at 3 issue slots instead of 4.  Each half is round-to-nearest: same bits.
+__device__ __forceinline__ void add4(float4& acc, const float4& v) {
+  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(acc.x), "+f"(acc.y) : "f"(v.x), "f"(v.y));
+#if GCS_SLAB_ADD_MODE == 2
+  asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(acc.z), "+f"(acc.w) : "f"(v.z), "f"(v.w));
+#else
+  acc.z += v.z;
+  acc.w += v.w;
+#endif
+}
+
+// Slab entry word: bits [23:4] = shared-memory address of the neighbour's row of the slab in 16-byte units (the lane ORs
+// its own column offset in; slab rows start on 128-byte boundaries), bit 31 - r = row r of the block has this neighbour.
+// No bit set = padding, or an entry of the neighbouring graph in a straddling block: a no-op that reads slab row 0.
+__device__ __forceinline__ uint32_t slab_word(uint32_t raw, int off, int n, int shift, uint32_t base) {
+  const int loc = static_cast<int>(raw >> 8) - off;
+  const uint32_t m = __brev(raw) & 0xF0000000u;
+  return (static_cast<unsigned>(loc) < static_cast<unsigned>(n) && m) ? (base + (static_cast<uint32_t>(loc) << shift)) | m : base;
+}
+
+template <int RB>
+__device__ __forceinline__ void scatter(float4 (&acc)[RB], const float4& v, uint32_t m) {
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+    if (r == 0 ? static_cast<int>(m) < 0 : (m & (0x80000000u >> r)) != 0u) add4(acc[r], v);
+}
+
+struct Out {
+  const float* R; int64_t ldr; float* Y; int64_t ldy; bool want_amax;
+};
+
+template <int RB>
+__device__ __forceinline__ float store_block(const Out& o, float4 (&acc)[RB], int b, int off, int end, int col, float mx) {
+  float* yrow = o.Y + static_cast<int64_t>(b) * RB * o.ldy + col;
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int row = b * RB + r;
+    if (row >= off && row < end) {
+      if (o.R) {                                     // Add()([z, out]): the skip operand joins after the aggregation
+        const float4 t = __ldg(reinterpret_cast<const float4*>(o.R + static_cast<int64_t>(row) * o.ldr + col));
+        acc[r].x += t.x; acc[r].y += t.y; acc[r].z += t.z; acc[r].w += t.w;
+      }
+      *reinterpret_cast<float4*>(yrow + r * o.ldy) = acc[r];
+      if (o.want_amax) mx = amax4(mx, acc[r]);
+    }
+  }
+  return mx;
+}
+
+// One gather pass of a warp over a staged graph: 2^LQ lanes per row block, each lane owns 4 columns; row blocks are
+// handed out through the stage's shared counter, (32 >> LQ) consecutive blocks per warp at a time.
+template <int RB, int LQ>
+__device__ __forceinline__ float gather_slab(const Meta& m, uint32_t slab, uint32_t sblk, uint32_t sent, int* counter,
+                                             const Out& o, float mx) {
+  constexpr int q = 1 << LQ, gpw = 32 >> LQ;
+  const int lane = threadIdx.x & 31;
+  const int quad = lane & (q - 1), gidx = lane >> LQ;
+  const uint32_t qoff = static_cast<uint32_t>(quad) << 4;
+  const int col = m.col0 + quad * 4;
+  const int end = m.off + m.n;
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, gpw);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= m.nb) break;
+    const int bl = base + gidx;
+    if (bl < m.nb) {
+      float4 acc[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int e0, e1;
+      asm volatile("ld.shared.s32 %0, [%2];\n\tld.shared.s32 %1, [%2 + 4];" : "=&r"(e0), "=&r"(e1) : "r"(sblk + 4u * bl));
+#ifdef GCS_SLAB_DEBUG
+      if ((e0 & 3) || (e1 & 3) || e0 < 0 || e1 < e0 || e1 > m.ent_words || (sent & 15u) || (slab & 127u)) {
+        printf("slab gather: bad block e0=%d e1=%d ent_words=%d bl=%d nb=%d n=%d off=%d lq=%d sent=%u slab=%u blk=%d\n", e0, e1,
+               m.ent_words, bl, m.nb, m.n, m.off, m.lq, sent, slab, (int)blockIdx.x);
+        __trap();
+      }
+#endif
+      uint32_t ea = sent + 4u * e0;
+      const uint32_t eb = sent + 4u * e1;
+      for (; ea < eb; ea += 16) {
+        const uint4 w = lds128u(ea);
+#ifdef GCS_SLAB_DEBUG
+        {
+          const uint32_t lo = slab, hi = slab + (static_cast<uint32_t>(m.n_up) << (LQ + 4));
+          const uint32_t a0 = w.x & kAddrMask, a1 = w.y & kAddrMask, a2 = w.z & kAddrMask, a3 = w.w & kAddrMask;
+          if (a0 < lo || a0 >= hi || a1 < lo || a1 >= hi || a2 < lo || a2 >= hi || a3 < lo || a3 >= hi) {
+            printf("slab gather: bad word %08x %08x %08x %08x slab=[%u,%u) ea=%u bl=%d blk=%d\n", w.x, w.y, w.z, w.w, lo, hi, ea, bl, (int)blockIdx.x);
+            __trap();
+          }
+        }
+#endif
+        const float4 v0 = lds128((w.x & kAddrMask) | qoff), v1 = lds128((w.y & kAddrMask) | qoff);
+        const float4 v2 = lds128((w.z & kAddrMask) | qoff), v3 = lds128((w.w & kAddrMask) | qoff);
+        scatter<RB>(acc, v0, w.x); scatter<RB>(acc, v1, w.y); scatter<RB>(acc, v2, w.z); scatter<RB>(acc, v3, w.w);
+      }
+      mx = store_block<RB>(o, acc, m.b_first + bl, m.off, end, col, mx);
+    }
+  }
+  return mx;
+}
+
+// The same pass without a slab: entries, block pointers and X rows straight from global memory (a graph whose
+// row-block entries do not fit a stage).  Each gather applies the prologue itself.
+template <int RB, int LQ, bool kTransform>
+__device__ __forceinline__ float gather_direct(const Meta& m, const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent,
+                                               const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale,
+                                               const float* __restrict__ shift, const float* __restrict__ alpha, int* counter,
+                                               const Out& o, float mx) {
+  constexpr int q = 1 << LQ, gpw = 32 >> LQ;
+  const int lane = threadIdx.x & 31;
+  const int quad = lane & (q - 1), gidx = lane >> LQ;
+  const int col = m.col0 + quad * 4;
+  const int end = m.off + m.n;
+  float4 sc, sh, al;
+  if (kTransform) {
+    sc = __ldg(reinterpret_cast<const float4*>(scale + col));
+    sh = __ldg(reinterpret_cast<const float4*>(shift + col));
+    al = __ldg(reinterpret_cast<const float4*>(alpha + col));
+  }
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, gpw);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= m.nb) break;
+    const int bl = base + gidx;
+    if (bl < m.nb) {
+      const int b = m.b_first + bl;
+      float4 acc[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int e0 = __ldg(blk_ptr + b), e1 = __ldg(blk_ptr + b + 1);
+      for (int e = e0; e < e1; ++e) {
+        const uint32_t raw = __ldg(ent + e);
+        const int c = static_cast<int>(raw >> 8);
+        if (c < m.off || c >= end) continue;          // the neighbouring graph's part of a straddling block
+        float4 v = __ldg(reinterpret_cast<const float4*>(X + static_cast<int64_t>(c) * ldx + col));
+        if (kTransform) {
+          v.x = bn_prelu(v.x, sc.x, sh.x, al.x);
+          v.y = bn_prelu(v.y, sc.y, sh.y, al.y);
+          v.z = bn_prelu(v.z, sc.z, sh.z, al.z);
+          v.w = bn_prelu(v.w, sc.w, sh.w, al.w);
+        }
+        scatter<RB>(acc, v, __brev(raw) & 0xF0000000u);
+      }
+      mx = store_block<RB>(o, acc, b, m.off, end, col, mx);
+    }
+  }
+  return mx;
+}
+
+template <int RB, bool kTransform>
+__global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
+    const __grid_constant__ Maps maps, const int32_t* __restrict__ graph_ptr, int n_graphs,
+    const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent, const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ alpha, const float* __restrict__ R, int64_t ldr, float* __restrict__ Y, int64_t ldy, int H,
+    int stage_bytes, int n_stages, float* __restrict__ amax, unsigned long long* __restrict__ dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // dbg (gcs_debug_slab_timing): per role {cycles waiting on its barrier, cycles working}, summed over warps and CTAs
+  unsigned long long t_wait = 0, t_work = 0, t0 = 0;
+#define GCS_TIC() do { if (dbg) t0 = clock64(); } while (0)
+#define GCS_TOC(acc) do { if (dbg) { const unsigned long long t1 = clock64(); acc += t1 - t0; t0 = t1; } } while (0)
+  // 128-byte aligned base inside the shared window: a lane ORs its column offset into the entry words
+  const uint32_t raw_base = smem_u32(smem_raw);
+  unsigned char* const smem = smem_raw + ((128u - (raw_base & 127u)) & 127u);
+  Header* const hd = reinterpret_cast<Header*>(smem);
+  unsigned char* const stage0 = smem + kHeaderBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = n_stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&hd->landed[s]), 1);
+      mbar_init(smem_u32(&hd->ready[s]), kXformWarps);
+      mbar_init(smem_u32(&hd->empty[s]), kGatherWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ncg = (H + kCols - 1) / kCols;           // the column groups of one graph are neighbouring work items:
+  const int64_t n_items = static_cast<int64_t>(n_graphs) * ncg;   // CTAs read whole rows of X together
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int g = static_cast<int>(w / ncg);
+      const int cg0 = static_cast<int>(w - static_cast<int64_t>(g) * ncg) * kCols;
+      const int cgw = min(kCols, H - cg0);
+      const int off = __ldg(graph_ptr + g);
+      const int n = __ldg(graph_ptr + g + 1) - off;
+      if (n <= 0) continue;
+      const int b_first = off / RB, nb = (off + n - 1) / RB - b_first + 1;
+      const int E0 = __ldg(blk_ptr + b_first), E1 = __ldg(blk_ptr + b_first + nb);
+      const int ent_words = E1 - E0;                  // a multiple of 4 (padded blocks)
+      const int blk_bytes = 4 * ((nb + 1 + 3) & ~3);
+      const int fixed = blk_bytes + 4 * ent_words;
+      const int nbox = (n + kBoxRows - 1) / kBoxRows, n_up = nbox * kBoxRows;
+      int cfit = kCols;
+      while (cfit >= 4 && static_cast<int64_t>(n_up) * cfit * 4 + fixed > stage_bytes) cfit >>= 1;
+      const bool direct = cfit < 4;
+      for (int c0 = 0; c0 < cgw;) {
+        int cw = direct ? kCols : cfit;
+        while (cw > cgw - c0) cw >>= 1;               // power of two >= 4 (H % 4 == 0)
+        const int lq = 31 - __clz(cw >> 2);
+        const int s = it % S;
+        GCS_TIC();
+        if (it >= S) mbar_wait(smem_u32(&hd->empty[s]), ((it / S) - 1) & 1);
+        GCS_TOC(t_wait);
+        unsigned char* const st = stage0 + static_cast<size_t>(s) * stage_bytes;
+        const int slab_bytes = n_up * cw * 4;
+        int32_t* const sblk = reinterpret_cast<int32_t*>(st + slab_bytes);
+        if (!direct) {
+#ifndef GCS_SLAB_NO_UNROLL
+#pragma unroll 8
+#endif
+          for (int i = lane; i <= nb; i += 32) sblk[i] = __ldg(blk_ptr + b_first + i) - E0;
+        }
+        if (lane == 0) {
+          Meta& m = hd->meta[s];
+          m.mode = direct ? 1 : 0; m.off = off; m.n = n; m.n_up = n_up; m.lq = lq; m.col0 = cg0 + c0;
+          m.b_first = b_first; m.nb = nb; m.e0 = E0; m.ent_words = ent_words;
+          hd->counter[s] = 0;
+        }
+        __syncwarp();
+        const uint32_t bar = smem_u32(&hd->landed[s]);
+        if (lane == 0) {
+          fence_proxy_async();                        // the slab was read / written through the generic proxy before
+          if (direct) mbar_arrive(bar);
+          else mbar_arrive_expect_tx(bar, static_cast<uint32_t>(slab_bytes + 4 * ent_words));
+        }
+        __syncwarp();
+#ifdef GCS_SLAB_DEBUG
+        if (lane == 0 && !direct) {
+          const uint32_t d = smem_u32(st + slab_bytes + blk_bytes);
+          if ((reinterpret_cast<uintptr_t>(ent + E0) & 15u) || (d & 15u) || (ent_words & 3) || ent_words < 0 || (smem_u32(st) & 127u) ||
+              slab_bytes + blk_bytes + 4 * ent_words > stage_bytes || (reinterpret_cast<uintptr_t>(&maps.m[lq]) & 63u)) {
+            printf("slab producer: E0=%d E1=%d ent=%p dst=%u st=%u slab_bytes=%d blk_bytes=%d n=%d n_up=%d cw=%d stage_bytes=%d map=%p\n", E0, E1,
+                   ent, d, smem_u32(st), slab_bytes, blk_bytes, n, n_up, cw, stage_bytes, &maps.m[lq]);
+            __trap();
+          }
+        }
+        __syncwarp();
+#endif
+        if (!direct) {
+          if (lane == 0 && ent_words > 0) bulk_g2s(smem_u32(st + slab_bytes + blk_bytes), ent + E0, 4u * ent_words, bar);
+          const uint32_t box_bytes = kBoxRows * cw * 4;
+          for (int bx = lane; bx < nbox; bx += 32)
+            tma_load_2d(smem_u32(st) + bx * box_bytes, &maps.m[lq], cg0 + c0, off + bx * kBoxRows, bar);
+        }
+        GCS_TOC(t_work);
+        ++it;
+        c0 += cw;
+      }
+    }
+    if (dbg && lane == 0) { atomicAdd(dbg + 0, t_wait); atomicAdd(dbg + 1, t_work); atomicAdd(dbg + 6, 1ull * it); }
+    const int s = it % S;                             // stop marker
+    if (it >= S) mbar_wait(smem_u32(&hd->empty[s]), ((it / S) - 1) & 1);
+    if (lane == 0) {
+      hd->meta[s].mode = -1;
+      mbar_arrive(smem_u32(&hd->landed[s]));
+    }
+  } else if (warp <= kXformWarps) {
+    // ------------------------------------------------------------------ prologue warps
+    const int tt = (warp - 1) * 32 + lane;
+    constexpr int NT = kXformWarps * 32;
+    for (int it = 0;; ++it) {
+      const int s = it % S;
+      GCS_TIC();
+      mbar_wait(smem_u32(&hd->landed[s]), (it / S) & 1);
+      GCS_TOC(t_wait);
+      const Meta m = hd->meta[s];
+      if (m.mode == 0) {
+        unsigned char* const st = stage0 + static_cast<size_t>(s) * stage_bytes;
+        const int slab_bytes = (m.n_up << m.lq) * 16;
+        const uint32_t slab = smem_u32(st);
+        uint32_t* const sent = reinterpret_cast<uint32_t*>(st + slab_bytes + 4 * ((m.nb + 1 + 3) & ~3));
+        uint4* const sent4 = reinterpret_cast<uint4*>(sent);
+        const int shift = m.lq + 4;
+#ifdef GCS_SLAB_SCALAR_CONV
+        for (int c = tt; c < m.ent_words; c += NT) sent[c] = slab_word(sent[c], m.off, m.n, shift, slab);
+#else
+#pragma unroll 2
+        for (int c = tt; c < (m.ent_words >> 2); c += NT) {
+          uint4 w = sent4[c];
+          w.x = slab_word(w.x, m.off, m.n, shift, slab);
+          w.y = slab_word(w.y, m.off, m.n, shift, slab);
+          w.z = slab_word(w.z, m.off, m.n, shift, slab);
+          w.w = slab_word(w.w, m.off, m.n, shift, slab);
+          sent4[c] = w;
+        }
+#endif
+        if (kTransform) {
+          const int col = m.col0 + (tt & ((1 << m.lq) - 1)) * 4;    // constant per thread: NT is a multiple of q
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + col));
+          const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + col));
+          float4* d = reinterpret_cast<float4*>(st) + tt;
+          float4* const dend = reinterpret_cast<float4*>(st) + (m.n << m.lq);
+#pragma unroll 4
+          for (; d < dend; d += NT) {
+            float4 v = *d;
+            v.x = bn_prelu(v.x, sc.x, sh.x, al.x);
+            v.y = bn_prelu(v.y, sc.y, sh.y, al.y);
+            v.z = bn_prelu(v.z, sc.z, sh.z, al.z);
+            v.w = bn_prelu(v.w, sc.w, sh.w, al.w);
+            *d = v;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&hd->ready[s]));
+      GCS_TOC(t_work);
+      if (m.mode < 0) break;
+    }
+    if (dbg && lane == 0) { atomicAdd(dbg + 2, t_wait); atomicAdd(dbg + 3, t_work); }
+  } else {
+    // ------------------------------------------------------------------ gather warps
+    const Out o{R, ldr, Y, ldy, amax != nullptr};
+    float mx = 0.f;
+    for (int it = 0;; ++it) {
+      const int s = it % S;
+      GCS_TIC();
+      mbar_wait(smem_u32(&hd->ready[s]), (it / S) & 1);
+      GCS_TOC(t_wait);
+      const Meta m = hd->meta[s];
+      if (m.mode < 0) break;
+      unsigned char* const st = stage0 + static_cast<size_t>(s) * stage_bytes;
+      const uint32_t slab = smem_u32(st);
+      const uint32_t sblk = slab + static_cast<uint32_t>(m.n_up << m.lq) * 16u;
+      const uint32_t sent = sblk + 4u * ((m.nb + 1 + 3) & ~3);
+      int* const ctr = &hd->counter[s];
+      if (m.mode == 0) {
+        switch (m.lq) {
+          case 3: mx = gather_slab<RB, 3>(m, slab, sblk, sent, ctr, o, mx); break;
+          case 2: mx = gather_slab<RB, 2>(m, slab, sblk, sent, ctr, o, mx); break;
+          case 1: mx = gather_slab<RB, 1>(m, slab, sblk, sent, ctr, o, mx); break;
+          default: mx = gather_slab<RB, 0>(m, slab, sblk, sent, ctr, o, mx); break;
+        }
+      } else {
+        switch (m.lq) {
+          case 3: mx = gather_direct<RB, 3, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
+          case 2: mx = gather_direct<RB, 2, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
+          case 1: mx = gather_direct<RB, 1, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
+          default: mx = gather_direct<RB, 0, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&hd->empty[s]));
+      GCS_TOC(t_work);
+    }
+    if (dbg && lane == 0) { atomicAdd(dbg + 4, t_wait); atomicAdd(dbg + 5, t_work); }
+    amax_commit(mx, amax);
+  }
+}
+
+int g_stages = 3;          // gcs_debug_set_param 10
+int g_stage_bytes = 0;     // gcs_debug_set_param 11 (0 = as large as the stages allow)
+int g_grid = 0;            // gcs_debug_set_param 12 (0 = one CTA per SM)
+unsigned long long* g_dbg = nullptr;   // gcs_debug_slab_timing: 8 device counters, see the kernel
+
+constexpr int kSmemMax = 232448;   // opt-in maximum per CTA on sm_100
+
+int stage_bytes() {
+  const int most = ((kSmemMax - kHeaderBytes - 128) / g_stages) & ~127;
+  return g_stage_bytes > 0 && g_stage_bytes < most ? (g_stage_bytes & ~127) : most;
+}
+
+}  // namespace slab
+
+void slab_set_param(int id, int value) {
+  if (id == 10 && value >= 2 && value <= slab::kMaxStages) slab::g_stages = value;
+  if (id == 11 && value >= 0) slab::g_stage_bytes = value;
+  if (id == 12 && value >= 0) slab::g_grid = value;
+}
+
+}  // namespace gcs
+
+using namespace gcs;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// X [n_rows, H] (row pitch ldx) as 2-D tensors with boxes of kBoxRows rows x 4 / 8 / 16 / 32 columns, rows dense in
+// shared memory (no swizzle); rows past n_rows read as zeros.
+int make_maps(slab::Maps* maps, const float* X, int64_t n_rows, int H, int64_t ldx) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  for (int k = 0; k < 4; ++k) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(n_rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldx) * sizeof(float)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(4 << k), static_cast<cuuint32_t>(slab::kBoxRows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled (slab) failed with CUresult %d", static_cast<int>(r));
+  }
+  return GCS_OK;
+}
+
+template <int RB>
+int launch_slab(int64_t n_rows, const int32_t* graph_ptr, int n_graphs, const int32_t* blk_ptr, const uint32_t* ent, const float* X,
+                int64_t ldx, const float* scale, const float* shift, const float* alpha, const float* R, int64_t ldr,
+                float* Y, int64_t ldy, int H, cudaStream_t st) {
+  alignas(64) slab::Maps maps;
+  GCS_TRY(make_maps(&maps, X, n_rows, H, ldx));
+  const int sb = slab::stage_bytes();
+  const int smem = slab::kHeaderBytes + 128 + slab::g_stages * sb;
+  const int64_t items = static_cast<int64_t>(n_graphs) * ((H + slab::kCols - 1) / slab::kCols);
+  int grid = slab::g_grid > 0 ? slab::g_grid : sm_count();
+  if (grid > items) grid = static_cast<int>(items);
+#define GCS_SLAB_LAUNCH(T)                                                                                             \
+  do {                                                                                                                 \
+    GCS_CUDA(cudaFuncSetAttribute(slab::spmm_slab_kernel<RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+    slab::spmm_slab_kernel<RB, T><<<grid, slab::kThreads, smem, st>>>(maps, graph_ptr, n_graphs, blk_ptr, ent, X, ldx, scale, \
+                                                                      shift, alpha, R, ldr, Y, ldy, H, sb, slab::g_stages, \
+                                                                      amax_sink().produce, slab::g_dbg);               \
+  } while (0)
+  if (scale) GCS_SLAB_LAUNCH(true); else GCS_SLAB_LAUNCH(false);
+#undef GCS_SLAB_LAUNCH
+  GCS_CHECK_LAUNCH("spmm_slab_kernel");
+  return GCS_OK;
+}
+
+// Whether the slab kernel takes the batch: the longest graph must fit a stage at the narrowest pass (4 columns), and the
+// typical graph should still get >= 64-byte rows (16 columns), otherwise the global-memory kernels are the better fit.
+bool slab_fits(int64_t n_rows, int32_t n_graphs, int32_t max_graph_nodes) {
+  if (n_graphs <= 0 || max_graph_nodes <= 0) return false;
+  const int64_t sb = slab::stage_bytes();
+  if ((static_cast<int64_t>(max_graph_nodes) + slab::kBoxRows) * 16 > sb) return false;
+  return (n_rows / n_graphs + slab::kBoxRows) * 64 <= sb;
+}
+
+}  // namespace
+
+// Profiling hook (not part of the drop-in surface): 8 uint64 device counters the slab kernel adds its per-role clock
+// cycles to - {producer wait, work, prologue wait, work, gather wait, work, items, -}; NULL switches it off.
+extern "C" void gcs_debug_slab_timing(unsigned long long* counters_dev) { slab::g_dbg = counters_dev; }
+
+extern "C" int64_t gcs_spmm_slab_stage_bytes(void) { return slab::stage_bytes(); }
+
+extern "C" int gcs_spmm_sum_graphs(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_graph_nodes,
+                                   const int32_t* rowptr, const int32_t* colidx, const int32_t* rb_blk_ptr,
+                                   const uint32_t* rb_ent, int32_t rb_height, int64_t n_rows, const float* X, int64_t ldx,
+                                   const float* scale, const float* shift, const float* alpha, const float* residual,
+                                   int64_t ldr, float* Y, int64_t ldy, int32_t H, gcs_stream stream) {
+  GCS_CHECK_ARG(n_rows >= 0 && H > 0, "gcs_spmm_sum_graphs: bad size (n_rows=%lld, H=%d)", (long long)n_rows, H);
+  if (n_rows == 0) return GCS_OK;
+  GCS_CHECK_ARG(rowptr && colidx && X && Y, "gcs_spmm_sum_graphs: null pointer");
+  GCS_CHECK_ARG(ldx >= H && ldy >= H, "gcs_spmm_sum_graphs: leading dimension smaller than H");
+  GCS_CHECK_ARG(!residual || ldr >= H, "gcs_spmm_sum_graphs: residual leading dimension smaller than H");
+  GCS_CHECK_ARG((scale != nullptr) == (shift != nullptr) && (scale != nullptr) == (alpha != nullptr),
+                "gcs_spmm_sum_graphs: scale/shift/alpha must be all NULL or all set");
+  GCS_CHECK_ARG((rb_blk_ptr != nullptr) == (rb_ent != nullptr), "gcs_spmm_sum_graphs: rb_blk_ptr and rb_ent go together");
+  GCS_CHECK_ARG(!rb_blk_ptr || rb_height == 2 || rb_height == 4, "gcs_spmm_sum_graphs: row-block height must be 2 or 4");
+  GCS_CHECK_ARG(X != Y, "gcs_spmm_sum_graphs: in-place aggregation is not defined");
+  GCS_CHECK_ARG(n_rows < INT32_MAX, "gcs_spmm_sum_graphs: n_rows exceeds int32 CSR range");
+  const bool vec_ok = (H % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
+                      (!scale || (aligned16(scale) && aligned16(shift) && aligned16(alpha))) &&
+                      (!residual || ((ldr % 4 == 0) && aligned16(residual)));
+  const int mode = spmm_mode();
+  const bool slab = graph_ptr && rb_blk_ptr && aligned16(rb_ent) && vec_ok && mode != 1 && mode != 2 &&
+                    slab_fits(n_rows, n_graphs, max_graph_nodes);
+  if (!slab) {
+    const bool rb4 = rb_blk_ptr && rb_height == 4;
+    return gcs_spmm_aggregate(rowptr, colidx, nullptr, rb4 ? rb_blk_ptr : nullptr, rb4 ? rb_ent : nullptr, n_rows, X, ldx,
+                              scale, shift, alpha, residual, ldr, Y, ldy, H, 0, stream);
+  }
+  cudaStream_t st = as_stream(stream);
+  if (rb_height == 2)
+    return launch_slab<2>(n_rows, graph_ptr, n_graphs, rb_blk_ptr, rb_ent, X, ldx, scale, shift, alpha, residual, ldr, Y, ldy, H, st);
+  return launch_slab<4>(n_rows, graph_ptr, n_graphs, rb_blk_ptr, rb_ent, X, ldx, scale, shift, alpha, residual, ldr, Y, ldy, H, st);
+}

@@ -121,8 +121,8 @@ class SparseAdjacency:
         self._indices = indices
         self._symmetric = symmetric
         self._t = None
-        self._rb4 = None
-        self._rb4_t = None
+        self._rb = {}
+        self._rb_t = {}
 
     @classmethod
     def from_indices(cls, indices, dense_shape, values=None):
@@ -167,19 +167,38 @@ class SparseAdjacency:
             self._symmetric = ops.csr_is_symmetric(self.rowptr, self.colidx)
         return self._symmetric
 
+    def rb(self, height: int = 4):
+        """(blk_ptr, ent): row-block form (2 or 4 rows per block) of the pattern for the aggregation kernels."""
+        if height not in self._rb:
+            self._rb[height] = ops.build_rb(self.rowptr, self.colidx, height)
+        return self._rb[height]
+
+    def rb_t(self, height: int = 4):
+        """Row-block form of the transposed pattern (the same arrays when symmetric)."""
+        if height not in self._rb_t:
+            self._rb_t[height] = self.rb(height) if self.symmetric else ops.build_rb(*self.transposed(), height)
+        return self._rb_t[height]
+
     @property
     def rb4(self):
-        """(blk_ptr, ent): RB4 row-block form of the pattern for the aggregation kernel."""
-        if self._rb4 is None:
-            self._rb4 = ops.build_rb4(self.rowptr, self.colidx)
-        return self._rb4
+        return self.rb(4)
 
     @property
     def rb4_t(self):
-        """RB4 form of the transposed pattern (the same arrays when symmetric)."""
-        if self._rb4_t is None:
-            self._rb4_t = self.rb4 if self.symmetric else ops.build_rb4(*self.transposed())
-        return self._rb4_t
+        return self.rb_t(4)
+
+    def slab_ok(self) -> bool:
+        """Whether the per-graph shared-memory aggregation kernel takes this batch (the rule of csrc/spmm_slab.cu)."""
+        if self.graph_ptr is None or self.max_graph_nodes <= 0:
+            return False
+        b = int(self.graph_ptr.shape[0]) - 1
+        cap = int(_lib.load().gcs_spmm_slab_stage_bytes())
+        return b > 0 and (self.max_graph_nodes + 32) * 16 <= cap and (self.n_rows // b + 32) * 64 <= cap
+
+    def rb_height(self) -> int:
+        """Block height the model entry points are given: 2 where the slab kernel runs on sparse rows (the gather comes
+        from shared memory, fewer predicated adds per entry win), 4 otherwise."""
+        return 2 if self.slab_ok() and self.nnz <= 20 * max(self.n_rows, 1) else 4
 
     def transposed(self):
         """(rowptr_t, colidx_t) of pattern(A)^T; the same arrays when symmetric."""

@@ -217,11 +217,13 @@ class GeneralGNN:
             graph_ptr, n_graphs = a.graph_ptr, a.graph_ptr.shape[0] - 1
         rp_t, ci_t = a.transposed() if need_transpose else (None, None)
         use_rb4 = self.use_rb4 and x.shape[0] < (1 << 24) and self.cfg.hidden % 4 == 0
-        rb4 = a.rb4 if use_rb4 else (None, None)
-        rb4_t = a.rb4_t if (use_rb4 and need_transpose) else (None, None)   # the same arrays when the pattern is symmetric
-        batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, 0, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
+        height = a.rb_height() if use_rb4 else 0
+        rb4 = a.rb(height) if use_rb4 else (None, None)
+        rb4_t = a.rb_t(height) if (use_rb4 and need_transpose) else (None, None)   # the same arrays when the pattern is symmetric
+        max_nodes = a.max_graph_nodes if a.graph_ptr is not None else (x.shape[0] if n_graphs == 1 else 0)
+        batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, height, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
                            ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None,
-                           ptr(seg), ptr(rb4[0]), ptr(rb4[1]), ptr(rb4_t[0]), ptr(rb4_t[1]))
+                           ptr(seg), ptr(rb4[0]), ptr(rb4[1]), ptr(rb4_t[0]), ptr(rb4_t[1]), int(max_nodes), 0)
         keep = (x, a, graph_ptr, rp_t, ci_t, rb4, rb4_t, seg)   # keep device buffers alive
         return batch, keep
 

@@ -241,18 +241,52 @@ def bn_prelu_bwd(da, h, mean, var, gamma, beta, alpha=None, eps=1e-3, want_dbias
 
 
 # ------------------------------------------------------------------ aggregation (K3/K7)
-def build_rb4(rowptr, colidx):
-    """RB4 row-block format of a CSR pattern -> (blk_ptr int32 [ceil(n/4)+1], ent uint32-as-int32 [nnz])."""
+def build_rb(rowptr, colidx, height: int = 4):
+    """Row-block format of a CSR pattern (block height 2 or 4) -> (blk_ptr int32 [ceil(n/height)+1],
+    ent uint32-as-int32 [nnz])."""
     torch = _t()
     lib = _lib.load()
+    if height not in (2, 4):
+        raise ValueError("row-block height must be 2 or 4")
     n = rowptr.shape[0] - 1
     nnz = colidx.shape[0]
-    blk_ptr = torch.empty((n + 3) // 4 + 1, dtype=torch.int32, device="cuda")
-    ent = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
-    ws = _ws(lib.gcs_spmm_rb4_workspace_bytes(n))
-    check(lib.gcs_spmm_build_rb4(ptr(rowptr), ptr(colidx), n, nnz, ptr(blk_ptr), ptr(ent), ptr(ws), ws.numel(),
-                                 stream_ptr()), "gcs_spmm_build_rb4")
+    blk_ptr = torch.empty((n + height - 1) // height + 1, dtype=torch.int32, device="cuda")
+    ent = torch.empty(max(nnz + 3 * ((n + height - 1) // height), 4), dtype=torch.int32, device="cuda")   # blocks are padded to 4 entries
+    ws = _ws(lib.gcs_spmm_rb_workspace_bytes(n, height))
+    check(lib.gcs_spmm_build_rb(ptr(rowptr), ptr(colidx), n, nnz, height, ptr(blk_ptr), ptr(ent), ptr(ws), ws.numel(),
+                                stream_ptr()), "gcs_spmm_build_rb")
     return blk_ptr, ent
+
+
+def build_rb4(rowptr, colidx):
+    return build_rb(rowptr, colidx, 4)
+
+
+def spmm_sum_graphs(graph_ptr, max_graph_nodes, rowptr, colidx, x, scale=None, shift=None, alpha=None, residual=None,
+                    out=None, rb=None, rb_height=0):
+    """The aggregation of a disjoint batch (gcs_spmm_sum_graphs): graph g owns rows / columns
+    [graph_ptr[g], graph_ptr[g+1]); each graph's slice of x is staged in shared memory.  ``rb`` = (blk_ptr, ent) from
+    ``build_rb(..., rb_height)`` or None (gathers walk the CSR).  Same results as ``spmm_sum``."""
+    torch = _t()
+    lib = _lib.load()
+    x, ldx = _mat(x, "x")
+    n, hdim = x.shape
+    if rowptr.shape[0] != n + 1:
+        raise ValueError(f"A has {rowptr.shape[0] - 1} rows but x has {n}")
+    ldr = 0
+    if residual is not None:
+        residual, ldr = _mat(residual, "residual")
+        if tuple(residual.shape) != (n, hdim):
+            raise ValueError("residual must have the shape of the output")
+    if out is None:
+        out = torch.empty(n, hdim, dtype=torch.float32, device="cuda")
+    out, ldy = _mat(out, "y")
+    bp, en = rb if rb is not None else (None, None)
+    n_graphs = graph_ptr.shape[0] - 1 if graph_ptr is not None else 0
+    check(lib.gcs_spmm_sum_graphs(ptr(graph_ptr), n_graphs, int(max_graph_nodes), ptr(rowptr), ptr(colidx), ptr(bp), ptr(en),
+                                  int(rb_height), n, ptr(x), ldx, ptr(scale), ptr(shift), ptr(alpha), ptr(residual), ldr,
+                                  ptr(out), ldy, hdim, stream_ptr()), "gcs_spmm_sum_graphs")
+    return out
 
 
 def spmm_sum(rowptr, colidx, x, scale=None, shift=None, alpha=None, out=None, rb4=None):

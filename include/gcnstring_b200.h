@@ -166,14 +166,20 @@ int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh,
  * pass scale = shift = alpha = NULL for f = identity (that is also the backward:
  * dX = pattern(A)^T . dY, called with the transposed CSR).  Neighbours are accumulated in
  * ascending column order per output row.
- * RB4 (optional): gcs_spmm_build_rb4 derives, once per batch, the row-block-of-4 format from
- * the CSR: per block of 4 consecutive rows the sorted union of their columns, each entry
- * (col << 8) | mask-of-rows.  Banded residue graphs share most neighbours between consecutive
- * rows, so a neighbour row is gathered and transformed once per block instead of once per row.
- * rb4_blk_ptr needs ceil(n_rows/4)+1 int32, rb4_ent nnz uint32 (upper bound), workspace
- * gcs_spmm_rb4_workspace_bytes(n_rows); n_rows < 2^24.  With rb4_* == NULL the CSR row kernel
- * runs; results are bit-identical.  Any matrix structure is accepted either way.
+ * Row-block format (optional): gcs_spmm_build_rb derives, once per batch, the row-block form of the CSR: per block of
+ * rb_height (2 or 4) consecutive rows the sorted union of their columns, each entry (col << 8) | mask-of-rows.  Banded
+ * residue graphs share most neighbours between consecutive rows, so a neighbour row is gathered once per block instead
+ * of once per row.  Every block is padded to a multiple of 4 entries (mask 0: no-ops) so that it starts on a 16-byte
+ * boundary.  rb_blk_ptr needs ceil(n_rows/rb_height)+1 int32, rb_ent nnz + 3*ceil(n_rows/rb_height) uint32 (upper
+ * bound; 16-byte aligned), workspace
+ * gcs_spmm_rb_workspace_bytes(n_rows, rb_height); n_rows < 2^24.  gcs_spmm_build_rb4 = height 4 (the only height the
+ * global-memory kernel behind gcs_spmm_sum / gcs_spmm_aggregate reads).  With rb_* == NULL the CSR row kernels run;
+ * results are bit-identical.  Any matrix structure is accepted either way.
  * --------------------------------------------------------------------------------- */
+int64_t gcs_spmm_rb_workspace_bytes(int64_t n_rows, int32_t rb_height);
+int gcs_spmm_build_rb(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz, int32_t rb_height,
+                      int32_t* rb_blk_ptr, uint32_t* rb_ent, void* workspace, int64_t workspace_bytes,
+                      gcs_stream stream);
 int64_t gcs_spmm_rb4_workspace_bytes(int64_t n_rows);
 int gcs_spmm_build_rb4(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz,
                        int32_t* rb4_blk_ptr, uint32_t* rb4_ent, void* workspace, int64_t workspace_bytes,
@@ -182,6 +188,22 @@ int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb
                  const uint32_t* rb4_ent, int64_t n_rows, const float* X, int64_t ldx,
                  const float* scale, const float* shift, const float* alpha, float* Y, int64_t ldy,
                  int32_t H, gcs_stream stream);
+
+/* The same aggregation for a DISJOINT BATCH (what DisjointLoader emits, gcn.py:316-317): pattern(A) is block-diagonal,
+ * graph g owns rows and columns [graph_ptr[g], graph_ptr[g+1]).  One thread block per (graph, 32 feature columns) stages
+ * that slice of X in shared memory - every element of X leaves HBM once, the BatchNorm+PReLU prologue is applied once
+ * per element - and serves all gathers of the graph from there.  max_graph_nodes = the longest graph of the batch
+ * (the loader knows it on the host; 0 = unknown).  Batches whose graphs do not fit a shared-memory slab (or
+ * graph_ptr == NULL, or rb_* == NULL) run on the global-memory kernels of gcs_spmm_aggregate.  An entry that leaves its graph's column
+ * range is ignored (a caller error).  rb_* / rb_height as above; residual as in gcs_spmm_aggregate.  Results are bit-identical to gcs_spmm_sum. */
+int64_t gcs_spmm_slab_stage_bytes(void); /* bytes of one shared-memory stage: a graph runs 4 << k columns wide when
+                                            n_nodes * (16 << k) + its row-block entries fit; the slab kernel takes a batch
+                                            when max_graph_nodes * 16 and (n_rows / n_graphs) * 64 are both <= this */
+int gcs_spmm_sum_graphs(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_graph_nodes, const int32_t* rowptr,
+                        const int32_t* colidx, const int32_t* rb_blk_ptr, const uint32_t* rb_ent, int32_t rb_height,
+                        int64_t n_rows, const float* X, int64_t ldx, const float* scale, const float* shift,
+                        const float* alpha, const float* residual, int64_t ldr, float* Y, int64_t ldy, int32_t H,
+                        gcs_stream stream);
 
 /* General form (SURVEY.md 8 f3 and the 'sum' skip connection of GeneralGNN.call):
  *   Y = agg_j( w_ij * f(X[j]) ) + residual
@@ -271,7 +293,7 @@ typedef struct gcs_model_config {
   int32_t message_passing;  /* L (default 4) */
   int32_t pre_process;      /* default 2 */
   int32_t post_process;     /* default 2 */
-  int32_t connectivity;     /* 1 = 'cat' (only value built) */
+  int32_t connectivity;     /* 0 = None (out = z), 1 = 'cat' (out = concat[z, out]), 2 = 'sum' (out = z + out) */
   int32_t pool;             /* 1 = 'sum', 0 = None (node-level output) */
   int32_t final_activation; /* 0 = linear, 1 = softmax */
   float bn_momentum;        /* 0.99 */
@@ -282,7 +304,7 @@ typedef struct gcs_batch {
   int64_t n_nodes;
   int64_t nnz;
   int32_t n_graphs;
-  int32_t reserved;
+  int32_t rb_height;        /* row-block height of rb4_* below: 2 or 4 (0 = 4) */
   const int32_t* rowptr;    /* [N+1]  CSR of pattern(A): row = target, col = source */
   const int32_t* colidx;    /* [nnz] */
   const int32_t* rowptr_t;  /* CSR of pattern(A)^T; may equal rowptr/colidx if symmetric; */
@@ -292,10 +314,12 @@ typedef struct gcs_batch {
   int64_t ldx;
   const float* y;           /* [B, C] one-hot; NULL for inference */
   const int64_t* seg_ids;       /* [N] graph id of every node (Spektral's i); needed by the pooled backward */
-  const int32_t* rb4_blk_ptr;   /* RB4 form of pattern(A) (gcs_spmm_build_rb4), or NULL */
+  const int32_t* rb4_blk_ptr;   /* row-block form of pattern(A) (gcs_spmm_build_rb, height rb_height), or NULL */
   const uint32_t* rb4_ent;
   const int32_t* rb4_blk_ptr_t; /* RB4 form of pattern(A)^T; may alias when symmetric; backward only */
   const uint32_t* rb4_ent_t;
+  int32_t max_graph_nodes;      /* longest graph of the batch (host-known), 0 = unknown: selects the shared-memory slab */
+  int32_t reserved;             /*   aggregation kernel (gcs_spmm_sum_graphs) when graph_ptr is set */
 } gcs_batch;
 
 /* Number of floats in the flat trainable / state buffers (layout: gcn-string_b200/params.py). */

@@ -336,7 +336,8 @@ def test_spmm_rb4_kernel_matches_row_kernel_bitwise(n_mean, H):
     blk_ptr, ent = (host(t) for t in a.rb4)
     ent = ent.view(np.uint32)
     rp, ci = host(a.rowptr), host(a.colidx)
-    assert blk_ptr[0] == 0 and blk_ptr.shape[0] == (n + 3) // 4 + 1 and blk_ptr[-1] <= a.nnz
+    assert blk_ptr[0] == 0 and blk_ptr.shape[0] == (n + 3) // 4 + 1 and blk_ptr[-1] <= a.nnz + 3 * ((n + 3) // 4)
+    assert np.all(blk_ptr % 4 == 0)                       # blocks are padded to 4 entries (mask 0 = no-op)
     for b in (0, 3, (n - 1) // 4):
         rows = range(4 * b, min(4 * b + 4, n))
         want = {}
@@ -344,6 +345,8 @@ def test_spmm_rb4_kernel_matches_row_kernel_bitwise(n_mean, H):
             for c in ci[rp[r]:rp[r + 1]]:
                 want[int(c)] = want.get(int(c), 0) | (1 << k)
         got = ent[blk_ptr[b]:blk_ptr[b + 1]]
+        assert all(int(e >> 8) in want for e in got)
+        got = got[(got & 255) != 0]
         assert [int(e >> 8) for e in got] == sorted(want) and [int(e & 255) for e in got] == [want[c] for c in sorted(want)]
     assert blk_ptr[-1] < 0.7 * a.nnz                      # banded graphs: well under one entry per edge
     z = x.astype(np.float64) * sc + sh
@@ -390,6 +393,88 @@ def test_spmm_rb4_arbitrary_structure():
     finally:
         lib.gcs_debug_set_spmm_mode(0)
     assert rel_err(host(y_rows), _spmm_ref(a, host(x))) < TOL
+
+
+def _block_diag_batch(rng, sizes, density):
+    """Disjoint batch of random (non-banded, directed) graphs of the given sizes; some rows empty."""
+    mats = []
+    for n in sizes:
+        d = (rng.random((n, n)) < density).astype(np.int64)
+        if n > 3:
+            d[rng.integers(0, n)] = 0                     # an empty row
+            d[rng.integers(0, n)] = 1                     # a full row
+        mats.append(sp.csr_matrix(d))
+    a = sp.block_diag(mats, format="csr")
+    a.sort_indices()
+    gp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    return a, gp
+
+
+@pytest.mark.parametrize("stages", [3, 2])
+@pytest.mark.parametrize("height", [2, 4])
+@pytest.mark.parametrize("H,sizes,slab_bytes", [
+    (256, [37, 1, 2, 3, 130, 5, 64, 7, 255], None),       # ragged graphs, blocks straddling graph boundaries
+    (48, [301, 17, 90], None),                            # last column group 16 wide
+    (20, [9, 33, 4], None),                               # column group of 20 = passes of 16 + 4
+    (64, [700, 40, 1300, 5], 32768),                      # small slab: passes of 8 and 4 columns for the long graphs
+    (512, [150, 151], None),
+])
+def test_spmm_slab_kernel_bitwise(stages, height, H, sizes, slab_bytes):
+    """The per-graph shared-memory kernel (gcs_spmm_sum_graphs) adds each row's neighbours in ascending column order
+    like the CSR row kernel: bit-identical results, with and without the prologue and the residual, written into a
+    column slice; also against the float64 oracle."""
+    lib = _lib.load()
+    rng = np.random.default_rng(H + height)
+    a, gp = _block_diag_batch(rng, sizes, 0.08)
+    n = a.shape[0]
+    x = rng.standard_normal((n, H)).astype(np.float32)
+    res = rng.standard_normal((n, H)).astype(np.float32)
+    sc, sh, al = (rng.uniform(0.5, 1.5, H).astype(np.float32), rng.normal(0, 0.5, H).astype(np.float32),
+                  rng.uniform(-0.3, 1.4, H).astype(np.float32))
+    rp, ci, gpd = dev(a.indptr.astype(np.int32)), dev(a.indices.astype(np.int32)), dev(gp)
+    rb = ops.build_rb(rp, ci, height)
+    try:
+        lib.gcs_debug_set_spmm_mode(1)
+        y_rows = ops.spmm_sum(rp, ci, dev(x), dev(sc), dev(sh), dev(al))
+        y_rows_plain = ops.spmm_sum(rp, ci, dev(x))
+    finally:
+        lib.gcs_debug_set_spmm_mode(0)
+    wide = torch.zeros(n, 3 * H, device="cuda")
+    try:
+        lib.gcs_debug_set_param(10, stages)
+        if slab_bytes:
+            lib.gcs_debug_set_param(11, slab_bytes)      # small stages: narrow passes; entries that do not fit: direct gather
+        y = ops.spmm_sum_graphs(gpd, max(sizes), rp, ci, dev(x), dev(sc), dev(sh), dev(al), out=wide[:, H:2 * H], rb=rb,
+                                rb_height=height).clone()
+        y_plain = ops.spmm_sum_graphs(gpd, max(sizes), rp, ci, dev(x), rb=rb, rb_height=height)
+        y_res = ops.spmm_sum_graphs(gpd, max(sizes), rp, ci, dev(x), dev(sc), dev(sh), dev(al), residual=dev(res), rb=rb,
+                                    rb_height=height)
+    finally:
+        lib.gcs_debug_set_param(11, 0)
+        lib.gcs_debug_set_param(10, 3)
+    assert torch.equal(y, y_rows) and torch.equal(y_plain, y_rows_plain)
+    assert torch.equal(y_res, y_rows + dev(res))
+    assert float(wide[:, :H].abs().max()) == 0.0 and float(wide[:, 2 * H:].abs().max()) == 0.0
+    z = x.astype(np.float64) * sc + sh
+    assert rel_err(host(y), _spmm_ref(a, np.where(z > 0, z, al * z))) < TOL
+
+
+def test_spmm_graphs_falls_back_without_slab():
+    """No graph_ptr / unknown graph lengths / graphs longer than a slab: the global-memory kernels run, same result."""
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    a, gp = _block_diag_batch(rng, [60, 500, 31], 0.05)
+    x = dev(rng.standard_normal((a.shape[0], 32)).astype(np.float32))
+    rp, ci = dev(a.indptr.astype(np.int32)), dev(a.indices.astype(np.int32))
+    ref = ops.spmm_sum(rp, ci, x)
+    rb2, rb4 = ops.build_rb(rp, ci, 2), ops.build_rb(rp, ci, 4)
+    assert torch.equal(ops.spmm_sum_graphs(None, 0, rp, ci, x, rb=rb4, rb_height=4), ref)
+    assert torch.equal(ops.spmm_sum_graphs(dev(gp), 0, rp, ci, x, rb=rb2, rb_height=2), ref)
+    try:
+        lib.gcs_debug_set_param(11, 4096)                # 500 nodes * 16 bytes > 4096
+        assert torch.equal(ops.spmm_sum_graphs(dev(gp), 500, rp, ci, x, rb=rb2, rb_height=2), ref)
+    finally:
+        lib.gcs_debug_set_param(11, 0)
 
 
 @pytest.mark.parametrize("H", [64, 6])
