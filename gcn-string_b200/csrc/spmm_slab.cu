@@ -320,9 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
         const int slab_bytes = n_up * cw * 4;
         int32_t* const sblk = reinterpret_cast<int32_t*>(st + slab_bytes);
         if (!direct) {
-#ifndef GCS_SLAB_NO_UNROLL
 #pragma unroll 8
-#endif
           for (int i = lane; i <= nb; i += 32) sblk[i] = __ldg(blk_ptr + b_first + i) - E0;
         }
         if (lane == 0) {
@@ -385,20 +383,16 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
         const uint32_t slab = smem_u32(st);
         uint32_t* const sent = reinterpret_cast<uint32_t*>(st + slab_bytes + 4 * ((m.nb + 1 + 3) & ~3));
         uint4* const sent4 = reinterpret_cast<uint4*>(sent);
-        const int shift = m.lq + 4;
-#ifdef GCS_SLAB_SCALAR_CONV
-        for (int c = tt; c < m.ent_words; c += NT) sent[c] = slab_word(sent[c], m.off, m.n, shift, slab);
-#else
+        const int word_shift = m.lq + 4;
 #pragma unroll 2
         for (int c = tt; c < (m.ent_words >> 2); c += NT) {
           uint4 w = sent4[c];
-          w.x = slab_word(w.x, m.off, m.n, shift, slab);
-          w.y = slab_word(w.y, m.off, m.n, shift, slab);
-          w.z = slab_word(w.z, m.off, m.n, shift, slab);
-          w.w = slab_word(w.w, m.off, m.n, shift, slab);
+          w.x = slab_word(w.x, m.off, m.n, word_shift, slab);
+          w.y = slab_word(w.y, m.off, m.n, word_shift, slab);
+          w.z = slab_word(w.z, m.off, m.n, word_shift, slab);
+          w.w = slab_word(w.w, m.off, m.n, word_shift, slab);
           sent4[c] = w;
         }
-#endif
         if (kTransform) {
           const int col = m.col0 + (tt & ((1 << m.lq) - 1)) * 4;    // constant per thread: NT is a multiple of q
           const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
