@@ -250,7 +250,8 @@ def build_rb(rowptr, colidx, height: int = 4):
         raise ValueError("row-block height must be 2 or 4")
     n = rowptr.shape[0] - 1
     nnz = colidx.shape[0]
-    blk_ptr = torch.empty((n + height - 1) // height + 1, dtype=torch.int32, device="cuda")
+    n_blk = (n + height - 1) // height
+    blk_ptr = torch.zeros(n_blk + 4, dtype=torch.int32, device="cuda")[:n_blk + 1]    # 3 words of slack: read in 16-byte units
     ent = torch.empty(max(nnz + 3 * ((n + height - 1) // height), 4), dtype=torch.int32, device="cuda")   # blocks are padded to 4 entries
     ws = _ws(lib.gcs_spmm_rb_workspace_bytes(n, height))
     check(lib.gcs_spmm_build_rb(ptr(rowptr), ptr(colidx), n, nnz, height, ptr(blk_ptr), ptr(ent), ptr(ws), ws.numel(),

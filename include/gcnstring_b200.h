@@ -170,8 +170,8 @@ int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh,
  * rb_height (2 or 4) consecutive rows the sorted union of their columns, each entry (col << 8) | mask-of-rows.  Banded
  * residue graphs share most neighbours between consecutive rows, so a neighbour row is gathered once per block instead
  * of once per row.  Every block is padded to a multiple of 4 entries (mask 0: no-ops) so that it starts on a 16-byte
- * boundary.  rb_blk_ptr needs ceil(n_rows/rb_height)+1 int32, rb_ent nnz + 3*ceil(n_rows/rb_height) uint32 (upper
- * bound; 16-byte aligned), workspace
+ * boundary.  rb_blk_ptr needs ceil(n_rows/rb_height)+1 int32 (allocate 3 more: gcs_spmm_sum_graphs copies it in
+ * 16-byte units), rb_ent nnz + 3*ceil(n_rows/rb_height) uint32 (upper bound); both 16-byte aligned; workspace
  * gcs_spmm_rb_workspace_bytes(n_rows, rb_height); n_rows < 2^24.  gcs_spmm_build_rb4 = height 4 (the only height the
  * global-memory kernel behind gcs_spmm_sum / gcs_spmm_aggregate reads).  With rb_* == NULL the CSR row kernels run;
  * results are bit-identical.  Any matrix structure is accepted either way.

@@ -1,5 +1,5 @@
 #!/bin/bash
 set -x
-python scripts/spmm_bench.py --mode slab4 --iters 2 --param 10 2 > gpurun_out/r02_slab4_plain.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:spmm_slab -s 3 -c 1 -o gpurun_out/r02_slab4p -f python scripts/spmm_bench.py --mode slab4 --iters 2 --param 10 2 > gpurun_out/r02_ncu_slab4p.log 2>&1
+python scripts/spmm_bench.py --mode slab2 --iters 2 > gpurun_out/r02_slab2_plain.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:spmm_slab -s 3 -c 1 -o gpurun_out/r02_slab2p -f python scripts/spmm_bench.py --mode slab2 --iters 2 > gpurun_out/r02_ncu_slab2p.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -3

@@ -451,7 +451,7 @@ def test_spmm_slab_kernel_bitwise(stages, height, H, sizes, slab_bytes):
                                     rb_height=height)
     finally:
         lib.gcs_debug_set_param(11, 0)
-        lib.gcs_debug_set_param(10, 3)
+        lib.gcs_debug_set_param(10, 2)
     assert torch.equal(y, y_rows) and torch.equal(y_plain, y_rows_plain)
     assert torch.equal(y_res, y_rows + dev(res))
     assert float(wide[:, :H].abs().max()) == 0.0 and float(wide[:, 2 * H:].abs().max()) == 0.0
