@@ -29,6 +29,9 @@
 #ifndef GCS_SLAB_ASM
 #define GCS_SLAB_ASM volatile
 #endif
+#ifndef GCS_SLAB_HELPERS
+#define GCS_SLAB_HELPERS 0
+#endif
 #ifndef GCS_SLAB_ADD_MODE
 #define GCS_SLAB_ADD_MODE 2   // 1 = FADD2 + 2 FADD per float4 (307 us at cfg2), 2 = 2 FADD2 (300 us)
 #endif
@@ -40,8 +43,11 @@ namespace slab {
 
 constexpr int kCols = 32;            // feature columns per work item
 constexpr int kThreads = 1024;
-constexpr int kXformWarps = 4;
-constexpr int kGatherWarps = 27;
+#ifndef GCS_SLAB_XFORM_WARPS
+#define GCS_SLAB_XFORM_WARPS 8   // measured at cfg2 (prologue / plain, us): 2 warps 318 / 268, 4: 289 / 260, 6: 289 / 256, 8: 284 / 252
+#endif
+constexpr int kXformWarps = GCS_SLAB_XFORM_WARPS;
+constexpr int kGatherWarps = 31 - kXformWarps;
 constexpr int kMaxStages = 3;
 constexpr int kHeaderBytes = 1024;
 constexpr int kBoxRows = 32;         // rows per TMA box: a graph's slab holds its row count rounded up to this
@@ -59,7 +65,8 @@ struct Meta {
   int blk_skip;    // the staged block pointers start blk_skip words before the graph's first block (16-byte aligned copy)
   int blk_words;   // staged block-pointer words (a multiple of 4)
 };
-struct Maps { CUtensorMap m[4]; };   // X as a 2-D tensor, boxes of kBoxRows rows x (4 << k) columns, k = 0..3
+constexpr int kBigBoxRows = 128;     // the bulk of a graph is fetched in boxes of 128 rows, the tail in boxes of kBoxRows
+struct Maps { CUtensorMap m[2][4]; };   // X as a 2-D tensor; boxes of kBoxRows ([0]) / kBigBoxRows ([1]) rows x (4 << k) columns
 
 struct Header {
   unsigned long long landed[kMaxStages], ready[kMaxStages], empty[kMaxStages];
@@ -88,6 +95,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // TMA bulk copy global -> shared (16-byte aligned, size a multiple of 16), completing on an mbarrier
@@ -168,9 +181,17 @@ __device__ __forceinline__ float store_block(const Out& o, float4 (&acc)[RB], in
 
 // One gather pass of a warp over a staged graph: 2^LQ lanes per row block, each lane owns 4 columns; row blocks are
 // handed out through the stage's shared counter, (32 >> LQ) consecutive blocks per warp at a time.
+// One round = (32 >> LQ) consecutive row blocks from the stage's counter.  A prologue warp that helps gathering passes the
+// `landed` barrier of the next stage (ybar != 0): once that stage has landed its prologue comes first.
+__device__ __forceinline__ int claim_round(int* counter, int gpw, uint32_t ybar, uint32_t ypar) {
+  int base = 0x7fffffff;
+  if ((threadIdx.x & 31) == 0 && !(ybar && mbar_test(ybar, ypar))) base = atomicAdd(counter, gpw);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+
 template <int RB, int LQ, bool kResidual>
 __device__ __forceinline__ float gather_slab(const Meta& m, uint32_t slab, uint32_t sblk, uint32_t sent, int* counter,
-                                             const Out& o, float mx) {
+                                             const Out& o, float mx, uint32_t ybar, uint32_t ypar) {
   constexpr int q = 1 << LQ, gpw = 32 >> LQ;
   const int lane = threadIdx.x & 31;
   const int quad = lane & (q - 1), gidx = lane >> LQ;
@@ -178,12 +199,12 @@ __device__ __forceinline__ float gather_slab(const Meta& m, uint32_t slab, uint3
   const int col = m.col0 + quad * 4;
   const int end = m.off + m.n;
   for (;;) {
-    // one round = (32 >> LQ) consecutive row blocks.  (Claiming the next round ahead of time to hide the atomic's
-    // latency was measured slower: a warp then sits on blocks that an idle warp could have taken.)
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, gpw);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    // (Claiming the next round ahead of time to hide the atomic's latency was measured slower: a warp then sits on
+    // blocks that an idle warp could have taken.)
+    const int base = claim_round(counter, gpw, ybar, ypar);
     if (base >= m.nb) break;
+    // (Handing the blocks out longest first, sorted by the prologue warps so that the blocks of a round run the same
+    // number of iterations, was measured: no gain - 281 / 254 us against 279 / 249 us.)
     const int bl = base + gidx;
     if (bl < m.nb) {
       float4 acc[RB];
@@ -213,7 +234,7 @@ template <int RB, int LQ, bool kTransform>
 __device__ __forceinline__ float gather_direct(const Meta& m, const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent,
                                                const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale,
                                                const float* __restrict__ shift, const float* __restrict__ alpha, int* counter,
-                                               const Out& o, float mx) {
+                                               const Out& o, float mx, uint32_t ybar, uint32_t ypar) {
   constexpr int q = 1 << LQ, gpw = 32 >> LQ;
   const int lane = threadIdx.x & 31;
   const int quad = lane & (q - 1), gidx = lane >> LQ;
@@ -226,9 +247,7 @@ __device__ __forceinline__ float gather_direct(const Meta& m, const int32_t* __r
     al = __ldg(reinterpret_cast<const float4*>(alpha + col));
   }
   for (;;) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, gpw);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    const int base = claim_round(counter, gpw, ybar, ypar);
     if (base >= m.nb) break;
     const int bl = base + gidx;
     if (bl < m.nb) {
@@ -285,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&hd->landed[s]), 1);
       mbar_init(smem_u32(&hd->ready[s]), kXformWarps);
-      mbar_init(smem_u32(&hd->empty[s]), kGatherWarps);
+      mbar_init(smem_u32(&hd->empty[s]), (GCS_SLAB_HELPERS ? kXformWarps : 0) + kGatherWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -340,12 +359,15 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
           while (cw > cgw - c0) cw >>= 1;             // power of two >= 4 (H % 4 == 0)
           const int lq = 31 - __clz(cw >> 2);
           const int s = it % S;
-          GCS_TIC();
-          if (it >= S) mbar_wait(smem_u32(&hd->empty[s]), ((it / S) - 1) & 1);
-          GCS_TOC(t_wait);
           unsigned char* const st = stage0 + static_cast<size_t>(s) * stage_bytes;
           const int slab_bytes = n_up * cw * 4;
           const uint32_t bar = smem_u32(&hd->landed[s]);
+          // boxes: lanes [0, nbig) fetch 128 rows each, the next nsmall lanes 32 rows each (rounds of 32 lanes)
+          const int nbig = n_up / kBigBoxRows, nsmall = (n_up - nbig * kBigBoxRows) / kBoxRows;
+          const uint32_t row_bytes = cw * 4;
+          GCS_TIC();
+          if (it >= S) mbar_wait(smem_u32(&hd->empty[s]), ((it / S) - 1) & 1);
+          GCS_TOC(t_wait);
           if (lane == 0) {
             Meta& m = hd->meta[s];
             m.mode = direct ? 1 : 0; m.off = off; m.n = n; m.n_up = n_up; m.lq = lq; m.col0 = cg0 + c0;
@@ -362,9 +384,11 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
           }
           __syncwarp();
           if (!direct) {
-            const uint32_t box_bytes = kBoxRows * cw * 4;
-            for (int bx = lane; bx < nbox; bx += 32)
-              tma_load_2d(smem_u32(st) + bx * box_bytes, &maps.m[lq], cg0 + c0, off + bx * kBoxRows, bar);
+            for (int bx = lane; bx < nbig + nsmall; bx += 32) {
+              const bool big = bx < nbig;
+              const int row = big ? bx * kBigBoxRows : nbig * kBigBoxRows + (bx - nbig) * kBoxRows;
+              tma_load_2d(smem_u32(st) + row * row_bytes, &maps.m[big ? 1 : 0][lq], cg0 + c0, off + row, bar);
+            }
           }
           GCS_TOC(t_work);
           ++it;
@@ -381,87 +405,96 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
       hd->meta[s].mode = -1;
       mbar_arrive(smem_u32(&hd->landed[s]));
     }
-  } else if (warp <= kXformWarps) {
-    // ------------------------------------------------------------------ prologue warps
+  } else {
+    // ------------------------------------------------------------------ consumers
+    // Warps 1..kXformWarps run the prologue of every stage (entry words -> shared addresses, f(x) in place); the rest
+    // gather.  (GCS_SLAB_HELPERS=1 lets the prologue warps gather as well until the next stage lands - measured slower,
+    // 306 / 273 us against 279 / 249 us: they only look for the next stage between rounds and the prologue starts late.)
+    const bool helper = warp <= kXformWarps;
     const int tt = (warp - 1) * 32 + lane;
     constexpr int NT = kXformWarps * 32;
-    for (int it = 0;; ++it) {
-      const int s = it % S;
-      GCS_TIC();
-      mbar_wait(smem_u32(&hd->landed[s]), (it / S) & 1);
-      GCS_TOC(t_wait);
-      const Meta m = hd->meta[s];
-      if (m.mode == 0) {
-        unsigned char* const st = stage0 + static_cast<size_t>(s) * stage_bytes;
-        const int slab_bytes = (m.n_up << m.lq) * 16;
-        const uint32_t slab = smem_u32(st);
-        uint32_t* const sent = reinterpret_cast<uint32_t*>(st + slab_bytes + 4 * m.blk_words);
-        uint4* const sent4 = reinterpret_cast<uint4*>(sent);
-        const int word_shift = m.lq + 4;
-#pragma unroll 2
-        for (int c = tt; c < (m.ent_words >> 2); c += NT) {
-          uint4 w = sent4[c];
-          w.x = slab_word(w.x, m.off, m.n, word_shift, slab);
-          w.y = slab_word(w.y, m.off, m.n, word_shift, slab);
-          w.z = slab_word(w.z, m.off, m.n, word_shift, slab);
-          w.w = slab_word(w.w, m.off, m.n, word_shift, slab);
-          sent4[c] = w;
-        }
-        if (kTransform) {
-          const int col = m.col0 + (tt & ((1 << m.lq) - 1)) * 4;    // constant per thread: NT is a multiple of q
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + col));
-          const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + col));
-          float4* d = reinterpret_cast<float4*>(st) + tt;
-          float4* const dend = reinterpret_cast<float4*>(st) + (m.n << m.lq);
-#pragma unroll 4
-          for (; d < dend; d += NT) {
-            float4 v = *d;
-            v.x = bn_prelu(v.x, sc.x, sh.x, al.x);
-            v.y = bn_prelu(v.y, sc.y, sh.y, al.y);
-            v.z = bn_prelu(v.z, sc.z, sh.z, al.z);
-            v.w = bn_prelu(v.w, sc.w, sh.w, al.w);
-            *d = v;
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&hd->ready[s]));
-      GCS_TOC(t_work);
-      if (m.mode < 0) break;
-    }
-    GCS_TREPORT(2, 3);
-  } else {
-    // ------------------------------------------------------------------ gather warps
     const Out o{R, ldr, Y, ldy, amax != nullptr};
     float mx = 0.f;
     for (int it = 0;; ++it) {
       const int s = it % S;
+      const uint32_t par = (it / S) & 1;
+      unsigned char* const st = stage0 + static_cast<size_t>(s) * stage_bytes;
+      if (helper) {
+        GCS_TIC();
+        mbar_wait(smem_u32(&hd->landed[s]), par);
+        GCS_TOC(t_wait);
+        const Meta m = hd->meta[s];
+        if (m.mode == 0) {
+          const int slab_bytes = (m.n_up << m.lq) * 16;
+          const uint32_t slab = smem_u32(st);
+          uint4* const sent4 = reinterpret_cast<uint4*>(st + slab_bytes + 4 * m.blk_words);
+          const int word_shift = m.lq + 4;
+#pragma unroll 2
+          for (int c = tt; c < (m.ent_words >> 2); c += NT) {
+            uint4 w = sent4[c];
+            w.x = slab_word(w.x, m.off, m.n, word_shift, slab);
+            w.y = slab_word(w.y, m.off, m.n, word_shift, slab);
+            w.z = slab_word(w.z, m.off, m.n, word_shift, slab);
+            w.w = slab_word(w.w, m.off, m.n, word_shift, slab);
+            sent4[c] = w;
+          }
+          if (kTransform) {
+            const int col = m.col0 + (tt & ((1 << m.lq) - 1)) * 4;    // constant per thread: NT is a multiple of q
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + col));
+            const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + col));
+            float4* d = reinterpret_cast<float4*>(st) + tt;
+            float4* const dend = reinterpret_cast<float4*>(st) + (m.n << m.lq);
+#pragma unroll 4
+            for (; d < dend; d += NT) {
+              float4 v = *d;
+              v.x = bn_prelu(v.x, sc.x, sh.x, al.x);
+              v.y = bn_prelu(v.y, sc.y, sh.y, al.y);
+              v.z = bn_prelu(v.z, sc.z, sh.z, al.z);
+              v.w = bn_prelu(v.w, sc.w, sh.w, al.w);
+              *d = v;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&hd->ready[s]));
+        GCS_TOC(t_work);
+        if (m.mode < 0) break;
+        if (!GCS_SLAB_HELPERS) continue;
+      }
       GCS_TIC();
-      mbar_wait(smem_u32(&hd->ready[s]), (it / S) & 1);
+      mbar_wait(smem_u32(&hd->ready[s]), par);
       GCS_TOC(t_wait);
       const Meta m = hd->meta[s];
       if (m.mode < 0) break;
-      unsigned char* const st = stage0 + static_cast<size_t>(s) * stage_bytes;
       const uint32_t slab = smem_u32(st);
       const uint32_t sblk = slab + static_cast<uint32_t>(m.n_up << m.lq) * 16u;
       const uint32_t sent = sblk + 4u * m.blk_words;
       int* const ctr = &hd->counter[s];
+      const uint32_t ybar = helper ? smem_u32(&hd->landed[(it + 1) % S]) : 0u;
+      const uint32_t ypar = ((it + 1) / S) & 1;
+#define GCS_GATHER_SLAB(LQ)                                                                          \
+  mx = R ? gather_slab<RB, LQ, true>(m, slab, sblk, sent, ctr, o, mx, ybar, ypar)                    \
+         : gather_slab<RB, LQ, false>(m, slab, sblk, sent, ctr, o, mx, ybar, ypar)
+#define GCS_GATHER_DIRECT(LQ) \
+  mx = gather_direct<RB, LQ, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx, ybar, ypar)
       if (m.mode == 0) {
         switch (m.lq) {
-          case 3: mx = R ? gather_slab<RB, 3, true>(m, slab, sblk, sent, ctr, o, mx) : gather_slab<RB, 3, false>(m, slab, sblk, sent, ctr, o, mx); break;
-          case 2: mx = R ? gather_slab<RB, 2, true>(m, slab, sblk, sent, ctr, o, mx) : gather_slab<RB, 2, false>(m, slab, sblk, sent, ctr, o, mx); break;
-          case 1: mx = R ? gather_slab<RB, 1, true>(m, slab, sblk, sent, ctr, o, mx) : gather_slab<RB, 1, false>(m, slab, sblk, sent, ctr, o, mx); break;
-          default: mx = R ? gather_slab<RB, 0, true>(m, slab, sblk, sent, ctr, o, mx) : gather_slab<RB, 0, false>(m, slab, sblk, sent, ctr, o, mx); break;
+          case 3: GCS_GATHER_SLAB(3); break;
+          case 2: GCS_GATHER_SLAB(2); break;
+          case 1: GCS_GATHER_SLAB(1); break;
+          default: GCS_GATHER_SLAB(0); break;
         }
       } else {
         switch (m.lq) {
-          case 3: mx = gather_direct<RB, 3, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
-          case 2: mx = gather_direct<RB, 2, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
-          case 1: mx = gather_direct<RB, 1, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
-          default: mx = gather_direct<RB, 0, kTransform>(m, blk_ptr, ent, X, ldx, scale, shift, alpha, ctr, o, mx); break;
+          case 3: GCS_GATHER_DIRECT(3); break;
+          case 2: GCS_GATHER_DIRECT(2); break;
+          case 1: GCS_GATHER_DIRECT(1); break;
+          default: GCS_GATHER_DIRECT(0); break;
         }
       }
+#undef GCS_GATHER_SLAB
+#undef GCS_GATHER_DIRECT
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&hd->empty[s]));
       GCS_TOC(t_work);
@@ -515,17 +548,17 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// X [n_rows, H] (row pitch ldx) as 2-D tensors with boxes of kBoxRows rows x 4 / 8 / 16 / 32 columns, rows dense in
-// shared memory (no swizzle); rows past n_rows read as zeros.
+// X [n_rows, H] (row pitch ldx) as 2-D tensors with boxes of kBoxRows / kBigBoxRows rows x 4 / 8 / 16 / 32 columns, rows
+// dense in shared memory (no swizzle); rows past n_rows read as zeros.
 int make_maps(slab::Maps* maps, const float* X, int64_t n_rows, int H, int64_t ldx) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 8; ++k) {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(n_rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldx) * sizeof(float)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(4 << k), static_cast<cuuint32_t>(slab::kBoxRows)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(4 << (k & 3)), static_cast<cuuint32_t>(k < 4 ? slab::kBoxRows : slab::kBigBoxRows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+    CUresult r = fn(&maps->m[k >> 2][k & 3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(GCS_ERR_CUDA, "cuTensorMapEncodeTiled (slab) failed with CUresult %d", static_cast<int>(r));

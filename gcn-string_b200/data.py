@@ -196,9 +196,9 @@ class SparseAdjacency:
         return b > 0 and (self.max_graph_nodes + 32) * 16 <= cap and (self.n_rows // b + 32) * 64 <= cap
 
     def rb_height(self) -> int:
-        """Block height the model entry points are given: 2 where the slab kernel runs on sparse rows (the gather comes
-        from shared memory, fewer predicated adds per entry win), 4 otherwise."""
-        return 2 if self.slab_ok() and self.nnz <= 20 * max(self.n_rows, 1) else 4
+        """Block height the model entry points are given: 4 rows per block is the faster format at every width and
+        degree of the cfg4 sweep (profiles/r02_cfg4_spmm_sweep.jsonl; 2 rows per block only ties at degree 4)."""
+        return 4
 
     def transposed(self):
         """(rowptr_t, colidx_t) of pattern(A)^T; the same arrays when symmetric."""
