@@ -91,7 +91,11 @@ _DEBUG = {"gcs_debug_set_spmm_mode": (None, [I32]),
           "gcs_debug_set_gemm_mode": (None, [I32]),
           "gcs_debug_launch_count": (ctypes.c_longlong, []),
           "gcs_debug_profile_begin": (None, []),
-          "gcs_debug_profile_end": (c_int32, [ctypes.c_char_p, c_int32])}
+          "gcs_debug_profile_end": (c_int32, [ctypes.c_char_p, c_int32]),
+          "gcs_debug_slab_timing": (None, [P]),
+          "gcs_debug_prelu_branch": (c_int32, [P, I64, P, P, P, P, F32, I64, I32, P, P]),
+          "gcs_model_debug_block_buffers": (c_int32, [POINTER(ModelConfig), I64, I32, I32, POINTER(I64), POINTER(I64),
+                                                      POINTER(I64), POINTER(I32)])}
 
 _lib = None
 

@@ -638,3 +638,34 @@ extern "C" int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, i
   }
   return GCS_OK;
 }
+
+// Test hook (not part of the drop-in surface): the PReLU branch every element takes in the BatchNorm backward above,
+// computed with the same float32 expressions (xhat = (h - mean) * rsqrt(var + eps); z = fma(gamma, xhat, beta)):
+// out[r, c] = 1 for z > 0, -1 for z < 0, 0 for z == 0.  The parity tests hand it to the float64 oracle so that both
+// sides differentiate the same branch of the activation at inputs within rounding of its kink.
+namespace gcs {
+__global__ void prelu_branch_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ mean,
+                                    const float* __restrict__ var, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float eps, int64_t M, int C, int8_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  const int64_t r = i / C;
+  const int c = static_cast<int>(i - r * C);
+  const float rs = __frsqrt_rn(__ldg(var + c) + eps);
+  const float xhat = (__ldg(h + r * ldh + c) - __ldg(mean + c)) * rs;
+  const float z = fmaf(__ldg(gamma + c), xhat, __ldg(beta + c));
+  out[i] = z > 0.f ? 1 : (z < 0.f ? -1 : 0);
+}
+}  // namespace gcs
+
+extern "C" int gcs_debug_prelu_branch(const float* h, int64_t ldh, const float* mean, const float* var, const float* gamma,
+                                      const float* beta, float eps, int64_t M, int32_t C, int8_t* out, gcs_stream stream) {
+  GCS_CHECK_ARG(h && mean && var && gamma && beta && out && M >= 0 && C > 0 && ldh >= C, "gcs_debug_prelu_branch: bad argument");
+  if (M == 0) return GCS_OK;
+  const int64_t n = M * C;
+  gcs::prelu_branch_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, gcs::as_stream(stream)>>>(h, ldh, mean, var, gamma, beta,
+                                                                                                     eps, M, C, out);
+  GCS_CHECK_LAUNCH("prelu_branch_kernel");
+  return GCS_OK;
+}
+

@@ -630,3 +630,24 @@ extern "C" int gcs_model_backward(const gcs_model_config* cfg, const float* para
     return fail(GCS_ERR_WORKSPACE, "gcs_model_backward: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
   return run_backward(*cfg, p, params, grads, *batch, dlogits, stream);
 }
+
+// Test hook (not part of the drop-in surface): where a training-mode forward leaves block `block`'s pre-BatchNorm output
+// h [rows, width] and its statistics (mean | var | scale | shift, width floats each) inside the workspace (byte offsets).
+extern "C" int gcs_model_debug_block_buffers(const gcs_model_config* cfg, int64_t n_nodes, int32_t n_graphs, int32_t block,
+                                             int64_t* h_offset, int64_t* stat_offset, int64_t* rows, int32_t* width) {
+  GCS_TRY(check_config(cfg));
+  GCS_CHECK_ARG(h_offset && stat_offset && rows && width, "gcs_model_debug_block_buffers: null pointer");
+  Plan p;
+  int64_t total = 0;
+  char* const base = reinterpret_cast<char*>(256);
+  make_plan(*cfg, n_nodes, n_graphs, true, base, p, &total);
+  GCS_CHECK_ARG(block >= 0 && block < static_cast<int>(p.blocks.size()), "gcs_model_debug_block_buffers: no such block");
+  const int node_blocks = p.P + p.L;
+  const float* h = block < node_blocks ? p.h[block] : p.post_h[block - node_blocks];
+  *h_offset = reinterpret_cast<const char*>(h) - base;
+  *stat_offset = reinterpret_cast<const char*>(p.stat[block]) - base;
+  *rows = block < node_blocks ? n_nodes : p.rows_post;
+  *width = p.blocks[block].m_out;
+  return GCS_OK;
+}
+

@@ -450,11 +450,16 @@ class DisjointLoader:
         self._n = packed.n_graphs
         self._order = np.arange(self._n, dtype=np.int64)
         self._order_dev = None
+        self._order_epoch = -1
         self._generator = self._generate()
 
     @property
     def steps_per_epoch(self) -> int:
-        return int(np.ceil(self._n / self.batch_size))
+        """ceil(len / batch_size) as upstream; under data parallelism a short last batch with fewer graphs than ranks is
+        dropped on EVERY rank (each rank decides from the global slice, so no rank enters the gradient all-reduce
+        alone)."""
+        full, tail = divmod(self._n, self.batch_size)
+        return full + (1 if tail >= max(self.world_size, 1) else 0)
 
     def __len__(self):
         return self.steps_per_epoch
@@ -484,43 +489,50 @@ class DisjointLoader:
         return lo, lo + base + (1 if self.rank < rem else 0)
 
     def _slices(self):
-        """(device ids, host ids, global batch size) of every step, epoch after epoch."""
-        torch = _lib.require_cuda()
+        """(epoch, lo, hi, host ids, global batch size) of every step, epoch after epoch.  Nothing is uploaded here:
+        the device copies of the ids are made by _launch on the stream the batching kernels run on."""
         epochs = np.inf if self.epochs is None or self.epochs == -1 else self.epochs
         epoch = 0
         while epoch < epochs:
             epoch += 1
             if self.shuffle:
                 np.random.shuffle(self._order)
-            if self.shuffle or self._order_dev is None:
-                # pinned staging + asynchronous copy: a pageable .cuda() blocks the host until the device has drained
-                # everything queued before it, once per epoch
-                staged = torch.from_numpy(self._order.copy()).pin_memory()
-                self._order_dev = staged.cuda(non_blocking=True)
-                self._order_staged = staged            # keep the pinned buffer alive until the copy has run
             order_host = self._order.copy()
-            for b in range(self.steps_per_epoch):
+            for b in range(int(np.ceil(self._n / self.batch_size))):
                 start = b * self.batch_size
                 stop = min(start + self.batch_size, self._n)
+                if stop - start < self.world_size:
+                    continue                       # a tail shorter than the number of ranks: dropped by every rank alike
                 lo, hi = self._slices_of_rank(start, stop)
-                if hi <= lo:
-                    raise RuntimeError("a data-parallel rank received an empty shard; use batch_size >= world_size")
                 if self.balance == "nnz" and self.world_size > 1:
                     from .distributed import balanced_shard
                     ids = order_host[start:stop]
                     cost = self.store.h_n_edges[ids] + 4 * self.store.h_n_nodes[ids]
                     mine = np.ascontiguousarray(balanced_shard(ids, cost, self.rank, self.world_size))
-                    yield torch.from_numpy(mine).pin_memory().cuda(non_blocking=True), mine, stop - start
+                    yield epoch, None, None, mine, stop - start, order_host
                 else:
-                    yield self._order_dev[lo:hi], order_host[lo:hi], stop - start
+                    yield epoch, lo, hi, order_host[lo:hi], stop - start, order_host
 
     def _launch(self, item, stream):
-        """Enqueue upload + batching kernels for one step on `stream`."""
+        """Enqueue upload + batching kernels for one step on `stream`.  The graph ids go to the device on the SAME
+        stream (pinned staging, asynchronous copy): the batching kernels that read them are ordered behind the copy by
+        the stream itself, whichever stream the training step runs on."""
         torch = _lib.require_cuda()
-        ids_dev, ids_host, global_count = item
+        epoch, lo, hi, ids_host, global_count, order_host = item
         with torch.cuda.stream(stream):
+            if lo is None:                                     # work-balanced shard: its own id list
+                staged = torch.from_numpy(ids_host).pin_memory()
+                ids_dev = staged.cuda(non_blocking=True)
+            else:
+                if self._order_epoch != epoch:                 # one upload of the epoch's permutation, then slices of it
+                    self._order_staged = torch.from_numpy(order_host).pin_memory()
+                    self._order_dev = self._order_staged.cuda(non_blocking=True)
+                    self._order_epoch = epoch
+                staged = self._order_staged                    # pinned buffers stay alive until their copy has run
+                ids_dev = self._order_dev[lo:hi]
             x, a, i, y = self.store.batch(ids_dev, ids_host, want_coo=self.want_coo)
             a.global_batch_graphs = global_count
+            a._ids_keepalive = (ids_dev, staged)
             event = torch.cuda.Event()
             event.record(stream)
         return (x, a, i, y), event

@@ -59,12 +59,14 @@ def _block_fwd(blk, x, training, eps):
     return a, dict(x=x, h=h, mean=mean, var=var, rstd=rstd, z=z)
 
 
-def _block_bwd(blk, c, da, grads, need_dx=True):
-    """Training-mode backward of one block; writes into the flat ``grads``."""
+def _block_bwd(blk, c, da, grads, need_dx=True, branch=None):
+    """Training-mode backward of one block; writes into the flat ``grads``.  ``branch`` (int8 [rows, width]: 1 / -1 / 0)
+    overrides the side of PReLU's kink every element is differentiated on - see loss_and_grads."""
     sp_ = blk.spec
     z = c["z"]
     if blk.alpha is not None:
-        slope = np.where(z > 0, 1.0, np.where(z < 0, blk.alpha, 0.0))
+        side = np.sign(z) if branch is None else branch
+        slope = np.where(side > 0, 1.0, np.where(side < 0, blk.alpha, 0.0))
         dz = da * slope
         o, n = sp_.alpha
         grads[o:o + n] = (da * np.minimum(z, 0.0)).sum(0)
@@ -139,9 +141,15 @@ def accuracy(probs, y):
     return float((probs.argmax(1) == y.argmax(1)).mean())
 
 
-def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs):
+def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs, prelu_branch=None):
     """One training-mode forward + backward.  Returns dict(loss, acc, probs, grads (flat
-    float64, same layout as w), new_state (flat float64 moving statistics))."""
+    float64, same layout as w), new_state (flat float64 moving statistics)).
+
+    ``prelu_branch``: optional list (one entry per block, None for blocks without PReLU) of int8 arrays giving the
+    branch of PReLU (1: z > 0, -1: z < 0, 0: z == 0) another implementation differentiated each element on.  PReLU's
+    derivative jumps at 0, so an input within float32 rounding of 0 may land on either side in a float32
+    implementation; with the branches pinned the comparison measures arithmetic error only.  ``ctx['prelu_flips']``
+    counts the elements whose pinned branch differs from the float64 sign."""
     assert cfg.activation == "softmax" and cfg.pool == "sum" and cfg.connectivity in ("cat", "sum", None)
     y = y.astype(np.float64)
     probs, ctx = forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=True)
@@ -151,8 +159,14 @@ def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs):
     grads = np.zeros(w.shape[0], dtype=np.float64)
     d = (probs * y.sum(1, keepdims=True) - y) / B
     P, L, H = cfg.pre_process, cfg.message_passing, cfg.hidden
+    br = prelu_branch if prelu_branch is not None else [None] * len(blocks)
+    flips = 0
+    for bi, (blk, c) in enumerate(zip(blocks, caches)):
+        if br[bi] is not None and blk.alpha is not None:
+            flips += int((np.sign(c["z"]) != br[bi]).sum())
+    ctx["prelu_flips"] = flips
     for bi in range(len(blocks) - 1, P + L - 1, -1):
-        d = _block_bwd(blocks[bi], caches[bi], d, grads)
+        d = _block_bwd(blocks[bi], caches[bi], d, grads, branch=br[bi])
     dout = d[seg]                                       # grad of segment_sum
     for k in range(L - 1, -1, -1):
         bi = P + k
@@ -161,9 +175,9 @@ def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs):
         else:                                           # Add: the gradient reaches both operands; None: only z
             dz, dprev = dout, (dout if cfg.connectivity == "sum" else 0.0)
         da = spmm_sum(cols, rows, dz, x.shape[0])       # pattern(A)^T . dz
-        dout = dprev + _block_bwd(blocks[bi], caches[bi], da, grads)
+        dout = dprev + _block_bwd(blocks[bi], caches[bi], da, grads, branch=br[bi])
     for bi in range(P - 1, -1, -1):
-        dout = _block_bwd(blocks[bi], caches[bi], dout, grads, need_dx=bi > 0)
+        dout = _block_bwd(blocks[bi], caches[bi], dout, grads, need_dx=bi > 0, branch=br[bi])
     new_state = s.astype(np.float64).copy()
     mom = cfg.bn_momentum
     for blk, c in zip(blocks, caches):

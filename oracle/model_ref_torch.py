@@ -39,7 +39,7 @@ def unpack(specs, w, s, requires_grad=True):
     return out
 
 
-def _block(p, x, training, eps, stats=None):
+def _block(p, x, training, eps, stats=None, branch=None):
     h = x @ p["W"] + p["b"]
     if training:
         mean = h.mean(0)
@@ -51,35 +51,41 @@ def _block(p, x, training, eps, stats=None):
     inv = torch.rsqrt(var + eps) * p["gamma"]              # tf.nn.batch_normalization
     z = h * inv + (p["beta"] - mean * inv)
     if p["alpha"] is not None:
+        if branch is not None:
+            # PReLU with the side of the kink pinned per element (see model_ref_np.loss_and_grads): identical to the
+            # line below wherever sign(z) agrees with the pinned branch, i.e. everywhere but within rounding of 0
+            br = torch.as_tensor(branch)
+            return z * (br > 0).to(z.dtype) + p["alpha"] * z * (br < 0).to(z.dtype)
         return torch.relu(z) - p["alpha"] * torch.relu(-z)  # Keras PReLU
     return z
 
 
-def forward(cfg, params, x, rows, cols, seg, n_graphs, training, stats=None):
+def forward(cfg, params, x, rows, cols, seg, n_graphs, training, stats=None, prelu_branch=None):
     P, L = cfg.pre_process, cfg.message_passing
+    br = prelu_branch if prelu_branch is not None else [None] * len(params)
     out = x
-    for p in params[:P]:
-        out = _block(p, out, training, cfg.bn_epsilon, stats)
+    for k, p in enumerate(params[:P]):
+        out = _block(p, out, training, cfg.bn_epsilon, stats, br[k])
     n = x.shape[0]
-    for p in params[P:P + L]:
-        a = _block(p, out, training, cfg.bn_epsilon, stats)
+    for k, p in enumerate(params[P:P + L]):
+        a = _block(p, out, training, cfg.bn_epsilon, stats, br[P + k])
         msgs = a[cols]                                      # tf.gather -> [nnz, H]
         z = torch.zeros(n, a.shape[1], dtype=a.dtype).index_add_(0, rows, msgs)
         out = torch.cat([z, out], dim=1) if cfg.connectivity == "cat" else (z + out if cfg.connectivity == "sum" else z)
     if cfg.pool == "sum":
         out = torch.zeros(n_graphs, out.shape[1], dtype=out.dtype).index_add_(0, seg, out)
-    for p in params[P + L:]:
-        out = _block(p, out, training, cfg.bn_epsilon, stats)
+    for k, p in enumerate(params[P + L:]):
+        out = _block(p, out, training, cfg.bn_epsilon, stats, br[P + L + k])
     return out                                              # logits (pre-softmax)
 
 
-def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs):
+def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs, prelu_branch=None):
     params = unpack(specs, w, s)
     xt = torch.tensor(np.asarray(x, dtype=np.float32))
     rt, ct, st = (torch.tensor(np.asarray(v, dtype=np.int64)) for v in (rows, cols, seg))
     yt = torch.tensor(np.asarray(y, dtype=np.float32))
     stats = []
-    logits = forward(cfg, params, xt, rt, ct, st, n_graphs, True, stats)
+    logits = forward(cfg, params, xt, rt, ct, st, n_graphs, True, stats, prelu_branch)
     logp = torch.log_softmax(logits, dim=1)
     loss = -(yt * logp).sum(1).mean()
     loss.backward()
@@ -92,7 +98,12 @@ def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs):
             if n:
                 grads[o:o + n] = p[key].grad.reshape(-1).numpy()
     probs = torch.softmax(logits.detach(), dim=1).numpy()
-    return dict(loss=float(loss.detach()), probs=probs, grads=grads, stats=stats)
+    new_state = np.asarray(s, dtype=np.float32).copy()      # Keras moving statistics: moving -= (moving - batch) * (1 - momentum)
+    for p, (mean, var) in zip(params, stats):
+        for rng, old, batch in ((p["spec"].moving_mean, p["mm"], mean), (p["spec"].moving_variance, p["mv"], var)):
+            o, n = rng
+            new_state[o:o + n] = (old - (old - batch) * (1.0 - cfg.bn_momentum)).numpy()
+    return dict(loss=float(loss.detach()), probs=probs, grads=grads, stats=stats, new_state=new_state)
 
 
 def time_reference_path(cfg, specs, w, s, graphs, n_steps=3, warmup=1, train=True, lr=0.0002,
