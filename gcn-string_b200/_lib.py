@@ -77,6 +77,14 @@ PROTOTYPES = {
     "gcs_softmax_xent": (c_int32, [P, P, I32, I32, P, P, P, F32, P]),
     "gcs_sgd_step": (c_int32, [P, P, I64, F32, F32, P]),
     "gcs_adam_step": (c_int32, [P, P, P, P, I64, F64, F64, F64, F64, I64, F32, P]),
+    "gcs_comm_unique_id": (c_int32, [P]),
+    "gcs_comm_init": (c_int32, [P, I32, I32, POINTER(c_void_p)]),
+    "gcs_comm_destroy": (c_int32, [P]),
+    "gcs_comm_rank": (c_int32, [P]),
+    "gcs_comm_world_size": (c_int32, [P]),
+    "gcs_allreduce_grads": (c_int32, [P, P, I64, P]),
+    "gcs_allreduce_f64": (c_int32, [P, P, I64, P]),
+    "gcs_model_train_step_dp": (c_int32, [POINTER(ModelConfig), P, P, POINTER(Batch), F32, P, P, P, P, I64, P, P, P]),
     "gcs_model_num_params": (c_int64, [POINTER(ModelConfig)]),
     "gcs_model_num_state": (c_int64, [POINTER(ModelConfig)]),
     "gcs_model_workspace_bytes": (c_int64, [POINTER(ModelConfig), I64, I64, I32, I32]),

@@ -413,10 +413,18 @@ static int block_backward(const gcs_model_config& c, const Plan& p, int bi, cons
   return GCS_OK;
 }
 
+// Called by run_backward whenever a trailing range of the flat gradient buffer is final: [begin, end) in floats, the
+// ranges tile the buffer from its end to its start.  The data-parallel step uses it to start the all-reduce of the
+// layers already differentiated while the earlier layers are still in the backward.
+struct GradReady {
+  int (*fn)(void* user, int64_t begin, int64_t end);
+  void* user;
+};
+
 // Reverse pass given dlogits = dLoss/d(logits) [rows_post, C]; needs the activations a
 // training-mode run_forward left in the workspace.
 static int run_backward(const gcs_model_config& c, const Plan& p, const float* params, float* grads,
-                        const gcs_batch& bt, const float* dlogits, gcs_stream st) {
+                        const gcs_batch& bt, const float* dlogits, gcs_stream st, const GradReady* ready = nullptr) {
   const int H = p.H, Wc = p.Wc, L = p.L, P = p.P, Q = p.Q;
   const int64_t N = p.N, R = p.rows_post;
   const bool cat = c.connectivity == 1;
@@ -442,6 +450,13 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
     da = din;
     ldda = lddin;
   }
+  int64_t grads_final_from = p.blocks.back().off + p.blocks.back().count();   // everything from here on is final
+  auto notify = [&](int first_block) -> int {                // blocks first_block .. have all been differentiated
+    const int64_t begin = p.blocks[first_block].off;
+    if (ready && begin < grads_final_from) GCS_TRY(ready->fn(ready->user, begin, grads_final_from));
+    grads_final_from = begin < grads_final_from ? begin : grads_final_from;
+    return GCS_OK;
+  };
   AmaxScope node_scope(nullptr, p.amax + 1, p.amax);        // weight gradients: activations under amax[0], dh under amax[1]
   // ---- message passing, last layer first.  Block z_k of cat (columns [(L-1-k)H, (L-k)H)) is read by
   // the pool and by every later conv layer k' > k (rows [(k'-1-k)H, (k'-k)H) of its kernel).
@@ -482,6 +497,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
     GCS_TIMED("spmm_bwd", aggregate(bt, true, dz, lddz, nullptr, nullptr, nullptr, nullptr, 0, p.tmp_a, H, H, st));
     GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N, p.cat + static_cast<int64_t>(L - k) * H, Wc,
                            p.dhcat + static_cast<int64_t>(k) * H, ldd, nullptr, 0, 0, st));
+    if (k == L - 1 || k == (L - 1) / 2) GCS_TRY(notify(bi));   // two buckets inside the message-passing stack
   }
   // ---- pre-processing MLP: its output block (last H columns of cat) is read by the pool and by
   // every conv layer k' (rows [k'H, (k'+1)H) of its kernel)
@@ -502,6 +518,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
       GCS_TIMED("spmm_bwd", aggregate(bt, true, g, H, nullptr, nullptr, nullptr, nullptr, 0, p.tmp_a, H, H, st));
       GCS_TRY(block_backward(c, p, P + k, params, grads, p.tmp_a, H, p.h[P + k], H, N, emb(k), ld_emb, p.dhcat, H, g, H,
                              c.connectivity == 2 ? 1 : 0, st));
+      if (k == L - 1 || k == (L - 1) / 2) GCS_TRY(notify(P + k));
     }
     da_pre = g;
     ldda_pre = H;
@@ -529,6 +546,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
     da = p.tmp_a;
     ldda = H;
   }
+  GCS_TRY(notify(0));
   return GCS_OK;
 }
 
@@ -604,6 +622,63 @@ extern "C" int gcs_model_train_step(const gcs_model_config* cfg, const float* pa
                            grad_scale, stream));
 
   return run_backward(c, p, params, grads, bt, p.dlogits, stream);
+}
+
+// Data-parallel train step: gcs_model_train_step + the gradient all-reduce, started bucket by bucket on comm_stream as
+// the backward finishes trailing ranges of the flat gradient buffer, so that only the last bucket's reduction is exposed.
+// On return (asynchronously) `stream` waits for the reductions: whatever follows on it - the optimizer step - sees the
+// summed gradients.
+namespace {
+struct DpSync {
+  gcs_comm* comm; float* grads; cudaStream_t compute, comm_stream; cudaEvent_t ev[8]; int used;
+};
+int dp_bucket(void* user, int64_t begin, int64_t end) {
+  DpSync* d = static_cast<DpSync*>(user);
+  if (d->used >= 8) return fail(GCS_ERR_INVALID_ARGUMENT, "gcs_model_train_step_dp: too many gradient buckets");
+  cudaEvent_t e = d->ev[d->used++];
+  GCS_CUDA(cudaEventRecord(e, d->compute));
+  GCS_CUDA(cudaStreamWaitEvent(d->comm_stream, e, 0));
+  return gcs_allreduce_grads(d->comm, d->grads + begin, end - begin, d->comm_stream);
+}
+cudaEvent_t* dp_events() {           // per host thread: recorded and waited on within one call, reusable afterwards
+  thread_local cudaEvent_t ev[9];
+  thread_local bool made = false;
+  if (!made) {
+    for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    made = true;
+  }
+  return ev;
+}
+}  // namespace
+
+extern "C" int gcs_model_train_step_dp(const gcs_model_config* cfg, const float* params, float* state,
+                                       const gcs_batch* batch, float grad_scale, float* grads, float* probs,
+                                       float* loss_acc, void* workspace, int64_t workspace_bytes, gcs_stream stream,
+                                       gcs_comm* comm, gcs_stream comm_stream) {
+  GCS_TRY(check_config(cfg));
+  GCS_TRY(check_batch(*cfg, batch, true, true));
+  GCS_CHECK_ARG(cfg->final_activation == 1, "gcs_model_train_step_dp: the loss is categorical cross-entropy on a softmax output");
+  GCS_CHECK_ARG(params && state && grads && loss_acc && workspace && comm, "gcs_model_train_step_dp: null pointer");
+  GCS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "gcs_model_train_step_dp: workspace must be 256-byte aligned");
+  GCS_CHECK_ARG(comm_stream != stream, "gcs_model_train_step_dp: the collective needs its own stream");
+  const gcs_model_config& c = *cfg;
+  const gcs_batch& bt = *batch;
+  Plan p;
+  int64_t total = 0;
+  make_plan(c, bt.n_nodes, bt.n_graphs, true, workspace, p, &total);
+  if (workspace_bytes < total)
+    return fail(GCS_ERR_WORKSPACE, "gcs_model_train_step_dp: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
+  GCS_CHECK_ARG(p.rows_post < INT32_MAX, "gcs_model_train_step_dp: too many output rows");
+  GCS_TRY(run_forward(c, p, params, state, bt, true, stream));
+  GCS_TRY(gcs_softmax_xent(p.logits, bt.y, static_cast<int32_t>(p.rows_post), p.C, probs, loss_acc, p.dlogits, grad_scale, stream));
+  cudaEvent_t* ev = dp_events();
+  DpSync sync{comm, grads, as_stream(stream), as_stream(comm_stream), {}, 0};
+  for (int i = 0; i < 8; ++i) sync.ev[i] = ev[i];
+  GradReady ready{dp_bucket, &sync};
+  GCS_TRY(run_backward(c, p, params, grads, bt, p.dlogits, stream, &ready));
+  GCS_CUDA(cudaEventRecord(ev[8], as_stream(comm_stream)));
+  GCS_CUDA(cudaStreamWaitEvent(as_stream(stream), ev[8], 0));
+  return GCS_OK;
 }
 
 extern "C" int64_t gcs_model_logits_offset(const gcs_model_config* cfg, int64_t n_nodes, int32_t n_graphs,

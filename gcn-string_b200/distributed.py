@@ -100,6 +100,45 @@ def sync_batchnorm_hook(model, group=None):
     return fn
 
 
+class NativeComm:
+    """The library's own NCCL communicator (gcs_comm_init): rank 0 draws the 128-byte unique id and torch.distributed
+    (any backend) only carries it to the other ranks - the collectives themselves go through the C ABI
+    (gcs_allreduce_grads / gcs_model_train_step_dp), as a host without torch would issue them."""
+
+    def __init__(self, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        lib = _lib.load()
+        rank, ws = world()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_char * 128)()
+            _lib.check(lib.gcs_comm_unique_id(buf), "gcs_comm_unique_id")
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if ws > 1:
+            dev = ident.cuda() if dist.get_backend(group) == "nccl" else ident
+            dist.broadcast(dev, src=0, group=group)
+            ident = dev.cpu()
+        handle = ctypes.c_void_p()
+        raw = (ctypes.c_char * 128).from_buffer_copy(bytes(ident.numpy().tobytes()))
+        _lib.check(lib.gcs_comm_init(raw, rank, ws, ctypes.byref(handle)), "gcs_comm_init")
+        self.handle, self.rank, self.world_size = handle, rank, ws
+        self.stream = torch.cuda.Stream()                 # the collective's own stream (overlaps the backward)
+        self._lib = lib
+
+    def allreduce_grads(self, flat):
+        from . import _lib
+        _lib.check(self._lib.gcs_allreduce_grads(self.handle, flat.data_ptr(), flat.numel(), _lib.stream_ptr()), "gcs_allreduce_grads")
+        return flat
+
+    def close(self):
+        if self.handle:
+            self._lib.gcs_comm_destroy(self.handle)
+            self.handle = None
+
+
 class DataParallelTrainer:
     """train_step = local fused forward/backward (grad_scale = 1/global_batch) -> one flat
     all-reduce -> fused optimizer step, identical on every rank.
@@ -108,10 +147,14 @@ class DataParallelTrainer:
     3H+1 in the backward): the step then equals ONE single-device step on the union of the shards - same loss
     gradient, same BatchNorm state on every rank - instead of a count-weighted average of per-shard steps."""
 
-    def __init__(self, model, optimizer, group=None, sync_bn: bool = False):
+    def __init__(self, model, optimizer, group=None, sync_bn: bool = False, native_comm: bool = False):
+        """``native_comm=True``: the gradient all-reduce goes through the library's own NCCL communicator and is
+        started bucket by bucket during the backward (gcs_model_train_step_dp) instead of one torch.distributed
+        all-reduce after it."""
         self.model, self.optimizer, self.group = model, optimizer, group
         self.sync_bn = bool(sync_bn)
         self._synced = False
+        self.comm = NativeComm(group) if native_comm and world()[1] > 1 else None
 
     def _hooked(self, fn):
         """Run ``fn`` with the sync-BatchNorm hook installed (no-op for one process or sync_bn=False)."""
@@ -127,18 +170,18 @@ class DataParallelTrainer:
 
     def train_step(self, inputs, target, global_batch: Optional[int] = None):
         rank, ws = world()
-        if not self._synced and self.model.built:
+        if not self.model.built:                  # build before the first step: a dry run would move the BatchNorm statistics
+            from . import _lib
+            self.model.build(int(_lib.as_tensor(inputs[0]).shape[1]))
+        if not self._synced:
             broadcast_parameters(self.model, 0, self.group)
             self._synced = True
         a = inputs[1]
         if global_batch is None:
             global_batch = getattr(a, "global_batch_graphs", None) or target.shape[0] * ws
-        step = lambda: self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch))   # noqa: E731
+        step = lambda: self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch), comm=self.comm)   # noqa: E731
         loss_acc, probs = self._hooked(step)
-        if not self._synced:                      # first call built the model lazily
-            broadcast_parameters(self.model, 0, self.group)
-            self._synced = True
-            loss_acc, probs = self._hooked(step)
-        allreduce_gradients(self.model.grads, self.group)
+        if self.comm is None:
+            allreduce_gradients(self.model.grads, self.group)
         self.optimizer.apply_flat(self.model.params, self.model.grads)
         return loss_acc, probs

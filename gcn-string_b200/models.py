@@ -267,10 +267,13 @@ class GeneralGNN:
         check(lib.gcs_model_backward(self._c, ptr(self.params), ctx["batch"], ptr(dlogits), ptr(self.grads),
                                      ptr(ctx["ws"]), ctx["ws"].numel(), stream_ptr()), "gcs_model_backward")
 
-    def train_step_grads(self, inputs, target, grad_scale: Optional[float] = None):
+    def train_step_grads(self, inputs, target, grad_scale: Optional[float] = None, comm=None):
         """Fused training-mode forward + categorical cross-entropy + backward (one C call).
         Leaves the gradients in ``self.grads``; returns (loss_acc [2] device tensor = {loss,
-        accuracy}, probs [B, C]).  ``grad_scale`` defaults to 1/B (mean loss, gcn.py:335)."""
+        accuracy}, probs [B, C]).  ``grad_scale`` defaults to 1/B (mean loss, gcn.py:335).
+        ``comm`` (distributed.NativeComm): the data-parallel form - the gradients are SUM all-reduced over the
+        communicator, bucket by bucket on its own stream while the backward is still running
+        (gcs_model_train_step_dp); the current stream waits for the reductions."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         batch, keep = self._prepare(inputs, need_transpose=True)
@@ -284,8 +287,13 @@ class GeneralGNN:
         probs = torch.empty(rows, self.cfg.output, dtype=torch.float32, device="cuda")
         loss_acc = torch.empty(2, dtype=torch.float32, device="cuda")
         gs = 1.0 / rows if grad_scale is None else float(grad_scale)
-        check(lib.gcs_model_train_step(self._c, ptr(self.params), ptr(self.state), batch, gs, ptr(self.grads),
-                                       ptr(probs), ptr(loss_acc), ptr(ws), ws.numel(), stream_ptr()),
-              "gcs_model_train_step")
+        if comm is not None:
+            check(lib.gcs_model_train_step_dp(self._c, ptr(self.params), ptr(self.state), batch, gs, ptr(self.grads),
+                                              ptr(probs), ptr(loss_acc), ptr(ws), ws.numel(), stream_ptr(), comm.handle,
+                                              comm.stream.cuda_stream), "gcs_model_train_step_dp")
+        else:
+            check(lib.gcs_model_train_step(self._c, ptr(self.params), ptr(self.state), batch, gs, ptr(self.grads),
+                                           ptr(probs), ptr(loss_acc), ptr(ws), ws.numel(), stream_ptr()),
+                  "gcs_model_train_step")
         self._keep = (keep, y)
         return loss_acc, probs

@@ -140,6 +140,70 @@ def make_dataset(n_graphs: int, seed: int = 0, n_mean: int = 500, deg: int = 12,
     return PackedGraphs(node_off, rowptr, col, x, y)
 
 
+def concat_packed(parts: List[PackedGraphs]) -> PackedGraphs:
+    """Concatenate packed datasets (graph order = order of the parts)."""
+    if len(parts) == 1:
+        return parts[0]
+    node_off = [np.zeros(1, dtype=np.int64)]
+    rowptr = []
+    n0, e0 = 0, 0
+    for p in parts:
+        node_off.append(p.node_off[1:] + n0)
+        rowptr.append(p.rowptr[:-1] + e0)
+        n0 += int(p.node_off[-1])
+        e0 += int(p.rowptr[-1])
+    rowptr.append(np.array([e0], dtype=np.int64))
+    return PackedGraphs(np.concatenate(node_off), np.concatenate(rowptr), np.concatenate([p.col for p in parts]),
+                        np.concatenate([p.x for p in parts]), np.concatenate([p.y for p in parts]))
+
+
+def _make_range(args):
+    seed, g0, g1, n_mean, deg, n_feat, n_classes = args
+    rps, cols, xs = [], [], []
+    node_off = np.zeros(g1 - g0 + 1, dtype=np.int64)
+    e_off = 0
+    for k, gid in enumerate(range(g0, g1)):
+        rp, c, x = make_graph(seed, gid, n_mean, deg, n_feat)
+        node_off[k + 1] = node_off[k] + x.shape[0]
+        rps.append(rp[:-1] + e_off)
+        e_off += int(rp[-1])
+        cols.append(c)
+        xs.append(x)
+    y = np.zeros((g1 - g0, n_classes), dtype=np.float32)
+    y[np.arange(g1 - g0), np.arange(g0, g1) % n_classes] = 1.0
+    return PackedGraphs(node_off, np.concatenate(rps + [np.array([e_off], dtype=np.int64)]), np.concatenate(cols),
+                        np.concatenate(xs), y)
+
+
+def make_dataset_parallel(n_graphs: int, seed: int = 0, n_mean: int = 500, deg: int = 12, n_feat: int = 32,
+                          n_classes: int = 2, workers: int = 0) -> PackedGraphs:
+    """make_dataset over a process pool (the same graphs: every graph is seeded by its id).  workers = 0: the cores this
+    process may run on."""
+    import multiprocessing as mp
+    import os
+    workers = workers or len(os.sched_getaffinity(0))
+    if workers <= 1 or n_graphs < 4 * workers:
+        return make_dataset(n_graphs, seed, n_mean, deg, n_feat, n_classes)
+    chunk = -(-n_graphs // (4 * workers))
+    jobs = [(seed, g0, min(g0 + chunk, n_graphs), n_mean, deg, n_feat, n_classes) for g0 in range(0, n_graphs, chunk)]
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = pool.map(_make_range, jobs)
+    return concat_packed(parts)
+
+
+def tile_dataset(packed: PackedGraphs, n_graphs: int) -> PackedGraphs:
+    """The first n_graphs graphs of `packed` repeated end to end (a large epoch out of a smaller set of unique
+    synthetic graphs; labels and features repeat with them)."""
+    g = packed.n_graphs
+    reps = -(-n_graphs // g)
+    out = concat_packed([packed] * reps)
+    if out.n_graphs == n_graphs:
+        return out
+    n1 = int(out.node_off[n_graphs])
+    e1 = int(out.rowptr[n1])
+    return PackedGraphs(out.node_off[:n_graphs + 1], out.rowptr[:n1 + 1], out.col[:e1], out.x[:n1], out.y[:n_graphs])
+
+
 def pack_graphs(graphs) -> PackedGraphs:
     """Pack a list of per-graph objects exposing ``.x [n,F]``, ``.a`` (scipy sparse / dense
     [n,n]) and ``.y`` — what the reference's MyDataset.read returns (gcn.py:84-102) — into

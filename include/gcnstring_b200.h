@@ -37,7 +37,8 @@ enum gcs_status {
   GCS_ERR_INVALID_ARGUMENT = 1, /* bad shape / null pointer / misaligned */
   GCS_ERR_UNSUPPORTED = 2,      /* configuration outside the native subset */
   GCS_ERR_WORKSPACE = 3,        /* workspace too small */
-  GCS_ERR_CUDA = 4              /* a CUDA runtime call or launch failed */
+  GCS_ERR_CUDA = 4,             /* a CUDA runtime call or launch failed */
+  GCS_ERR_NCCL = 5              /* NCCL missing or a collective failed */
 };
 
 int gcs_version(void);
@@ -283,6 +284,25 @@ int gcs_adam_step(float* w, const float* g, float* m, float* v, int64_t n, doubl
                   double beta2, double eps, int64_t step, float grad_scale, gcs_stream stream);
 
 /* ---------------------------------------------------------------------------------
+ * C1  Data-parallel collective (the reference is single-process, this is the sharding the north star
+ * asks for).  Graphs shard across the GPUs of a node, every rank runs gcs_model_train_step with grad_scale =
+ * 1 / global_batch on its shard, then ONE SUM all-reduce of the flat gradient buffer (NCCL over NVLink / NVSwitch) and the
+ * fused optimizer step - identical parameters on every rank.  NCCL is bound at run time (dlopen libnccl.so.2).
+ *   gcs_comm_unique_id: rank 0 fills 128 bytes (ncclUniqueId) and hands them to the other ranks by any host channel.
+ *   gcs_comm_init:      collective; binds to the calling thread's current device.  One communicator per (process, GPU).
+ *   gcs_allreduce_grads / gcs_allreduce_f64: in place, enqueued on `stream`; f64 is what a synchronised-BatchNorm
+ *                       hook (gcs_set_allreduce_hook) forwards its statistics through.
+ * --------------------------------------------------------------------------------- */
+typedef struct gcs_comm gcs_comm;
+int gcs_comm_unique_id(void* id_host_128_bytes);
+int gcs_comm_init(const void* id_host_128_bytes, int32_t rank, int32_t world_size, gcs_comm** comm);
+int gcs_comm_destroy(gcs_comm* comm);
+int gcs_comm_rank(const gcs_comm* comm);
+int gcs_comm_world_size(const gcs_comm* comm);
+int gcs_allreduce_grads(gcs_comm* comm, float* grads, int64_t n, gcs_stream stream);
+int gcs_allreduce_f64(gcs_comm* comm, double* buf, int64_t n, gcs_stream stream);
+
+/* ---------------------------------------------------------------------------------
  * Whole-model entry points: spektral.models.GeneralGNN.__call__ (gcn.py:334 training,
  * :351 inference) and the GradientTape backward of gcn.py:333-337.
  * --------------------------------------------------------------------------------- */
@@ -340,6 +360,16 @@ int gcs_model_train_step(const gcs_model_config* cfg, const float* params, float
                          const gcs_batch* batch, float grad_scale, float* grads, float* probs,
                          float* loss_acc, void* workspace, int64_t workspace_bytes,
                          gcs_stream stream);
+
+/* The train step of one data-parallel rank: gcs_model_train_step with grad_scale = 1 / global_batch, plus the SUM
+ * all-reduce of `grads` over `comm`, issued on comm_stream in three buckets as the backward finishes trailing ranges of
+ * the flat gradient buffer (post-MLP + last GeneralConv layers first), so that the reduction of all but the last bucket
+ * overlaps the rest of the backward.  `stream` is made to wait for the reductions before anything enqueued after this
+ * call (the optimizer step) runs. */
+int gcs_model_train_step_dp(const gcs_model_config* cfg, const float* params, float* state,
+                            const gcs_batch* batch, float grad_scale, float* grads, float* probs,
+                            float* loss_acc, void* workspace, int64_t workspace_bytes, gcs_stream stream,
+                            gcs_comm* comm, gcs_stream comm_stream);
 
 /* Split form of the train step, for callers that compute the loss themselves (the
  * GradientTape pattern of gcn.py:333-337): gcs_model_forward(training=1) leaves the
