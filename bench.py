@@ -381,8 +381,11 @@ def run_b200(args):
 
     def make(device_resident, shuffle, **store_kw):
         np.random.seed(1234)
+        # host-resident arm without reshuffling: contiguous shards, so that a rank's graphs are ONE slice of the pinned
+        # arrays (plain cudaMemcpyAsync per step); everything else is work-balanced
+        bal = balance if (device_resident or shuffle) else None
         loader = g.DisjointLoader(ds, batch_size=B * world, epochs=None, shuffle=shuffle, symmetric=True, rank=rank,
-                                  world_size=world, balance=balance, device_resident=device_resident, **store_kw)
+                                  world_size=world, balance=bal, device_resident=device_resident, **store_kw)
         model = g.GeneralGNN(CLASSES, activation="softmax", hidden=hidden, message_passing=LAYERS, seed=0)
         model.build(N_FEAT)
         trainer = DataParallelTrainer(model, g.optimizers.SGD(learning_rate=sched), sync_bn=args.sync_bn,

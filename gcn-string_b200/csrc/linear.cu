@@ -227,6 +227,87 @@ __global__ void colsum_final_kernel(const double* __restrict__ ws, int splits, i
   db[c] = static_cast<float>(s);
 }
 
+// Weight gradient of a THIN layer (K <= 32 input features: the first Dense of the pre-processing MLP, K = F = 16 / 32):
+// dW[K, N] = A[M, K]^T . dH[M, N].  The tensor-core kernels need K % 128 == 0 and the tiled FFMA kernel leaves 3/4 of
+// its 128-wide tile empty (676 us at cfg2).  Here a CTA of K/4 warps owns 128 columns x all K rows of dW for one slab
+// of the M rows: warp = 4 consecutive k, lane = 4 consecutive columns (16 accumulators); per row one 128-bit load of
+// dH (coalesced, 4 rows in flight), one broadcast LDS.128 of the staged A row and 16 FFMA.  Partials per row slab,
+// summed in slab order by split_reduce_kernel: deterministic.  8.4 GFLOP at cfg2 -> FFMA-bound at ~115 us.
+template <int K4>
+__global__ void __launch_bounds__(32 * K4) wgrad_thin_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ dH,
+                                                             int64_t ldh, float* __restrict__ part, int64_t M, int N,
+                                                             int64_t rows_per_split) {
+  constexpr int K = 4 * K4, CH = 64, NT = 32 * K4;
+  __shared__ __align__(16) float sA[CH][K];
+  const int t = threadIdx.x;
+  const int lane = t & 31, kg = t >> 5;               // columns 4*lane .. +3 of the CTA's 128, rows 4*kg .. +3 of dW
+  const int c = blockIdx.x * 128 + 4 * lane;
+  const int64_t r0 = blockIdx.y * rows_per_split;
+  const int64_t r1 = r0 + rows_per_split < M ? r0 + rows_per_split : M;
+  const bool live = c < N;                             // N % 4 == 0: a quad is inside or outside
+  float4 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fma4 = [&](const float4& a, const float4& d) {
+    acc[0].x = fmaf(a.x, d.x, acc[0].x); acc[0].y = fmaf(a.x, d.y, acc[0].y); acc[0].z = fmaf(a.x, d.z, acc[0].z); acc[0].w = fmaf(a.x, d.w, acc[0].w);
+    acc[1].x = fmaf(a.y, d.x, acc[1].x); acc[1].y = fmaf(a.y, d.y, acc[1].y); acc[1].z = fmaf(a.y, d.z, acc[1].z); acc[1].w = fmaf(a.y, d.w, acc[1].w);
+    acc[2].x = fmaf(a.z, d.x, acc[2].x); acc[2].y = fmaf(a.z, d.y, acc[2].y); acc[2].z = fmaf(a.z, d.z, acc[2].z); acc[2].w = fmaf(a.z, d.w, acc[2].w);
+    acc[3].x = fmaf(a.w, d.x, acc[3].x); acc[3].y = fmaf(a.w, d.y, acc[3].y); acc[3].z = fmaf(a.w, d.z, acc[3].z); acc[3].w = fmaf(a.w, d.w, acc[3].w);
+  };
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t rc = r0; rc < r1; rc += CH) {
+    const int rows = static_cast<int>(r1 - rc < CH ? r1 - rc : CH);
+    __syncthreads();                                   // the previous chunk has been consumed
+    for (int i = t; i < CH * K4; i += NT) {
+      const int rr = i / K4, q = i - rr * K4;
+      *reinterpret_cast<float4*>(&sA[rr][4 * q]) = rr < rows ? __ldg(reinterpret_cast<const float4*>(A + (rc + rr) * lda + 4 * q)) : zero;
+    }
+    __syncthreads();
+    const float* dcol = dH + rc * ldh + c;
+    if (!live) continue;                               // (uniform per warp: a warp's 32 quads are 128 consecutive columns)
+    if (rows == CH) {
+      // full chunk: groups of 4 rows, two register sets in ping-pong so that 8 dH loads are in flight behind the FMAs
+      float4 d0[4], d1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d0[u] = __ldg(reinterpret_cast<const float4*>(dcol + u * ldh));
+#pragma unroll
+      for (int rr = 0; rr < CH; rr += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d1[u] = __ldg(reinterpret_cast<const float4*>(dcol + (rr + 4 + u) * ldh));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fma4(*reinterpret_cast<const float4*>(&sA[rr + u][4 * kg]), d0[u]);
+        if (rr + 8 < CH) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d0[u] = __ldg(reinterpret_cast<const float4*>(dcol + (rr + 8 + u) * ldh));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fma4(*reinterpret_cast<const float4*>(&sA[rr + 4 + u][4 * kg]), d1[u]);
+      }
+    } else {
+      for (int rr = 0; rr < rows; ++rr)
+        fma4(*reinterpret_cast<const float4*>(&sA[rr][4 * kg]), __ldg(reinterpret_cast<const float4*>(dcol + rr * ldh)));
+    }
+  }
+  if (live) {
+    float* out = part + static_cast<int64_t>(blockIdx.y) * K * N + static_cast<int64_t>(4 * kg) * N + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(out + static_cast<int64_t>(k) * N) = acc[k];
+  }
+}
+
+static int g_thin = 1;     // gcs_debug_set_param 13: 0 sends thin layers to the tiled FFMA kernel again
+void set_thin_wgrad(int v) { g_thin = v; }
+static int thin_splits(int64_t M, int N) {
+  const int64_t colblocks = ceil_div(N, 128);
+  int64_t s = ceil_div(4LL * sm_count(), colblocks);
+  const int64_t max_s = ceil_div(M > 0 ? M : 1, 256);
+  if (s > max_s) s = max_s;
+  return static_cast<int>(s < 1 ? 1 : s);
+}
+static bool thin_ok(int64_t M, int K, int N, const float* A, int64_t lda, const float* dH) {
+  return g_thin && K <= 32 && K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && aligned16(A) && dH && M >= 4096 && N >= 64;
+}
+
 struct WeightSplit {
   int splits;
   int64_t r_per_split;
@@ -486,6 +567,10 @@ extern "C" int64_t gcs_linear_bwd_weight_workspace_bytes(int64_t M, int32_t K, i
   if (M < 0 || K <= 0 || N <= 0) return 0;
   const WeightSplit w = weight_split(M, K, N);
   int64_t part = round_up(static_cast<int64_t>(w.splits) * K * N * sizeof(float), 256);
+  if (K <= 32 && K % 4 == 0) {
+    const int64_t thin = round_up(static_cast<int64_t>(thin_splits(M, N)) * K * N * sizeof(float), 256);
+    if (thin > part) part = thin;
+  }
   if (K % 128 == 0 && N % 128 == 0) {
     const int64_t tcb = tc::wgrad_workspace_bytes(M, K, N);
     if (tcb > part) part = tcb;
@@ -532,6 +617,28 @@ extern "C" int gcs_linear_bwd_weight(const float* A, int64_t lda, const float* d
       GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, dW, M, K, N, 1, per, st, a_amax, b_amax));
     } else {
       GCS_TRY(tc::wgrad_launch(A, lda, dH, ldh, part, M, K, N, splits, per, st, a_amax, b_amax));
+      int64_t blocks = ceil_div(kn, 256);
+      if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+      split_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(part, splits, kn, dW);
+      GCS_CHECK_LAUNCH("split_reduce_kernel");
+    }
+  } else if (thin_ok(M, K, N, A, lda, dH) && ldh % 4 == 0 && aligned16(dH) && aligned16(dW) && aligned16(part)) {
+    const int splits = thin_splits(M, N);
+    const int64_t per = ceil_div(M, splits);
+    dim3 grid(static_cast<unsigned>(ceil_div(N, 128)), static_cast<unsigned>(splits));
+    float* dst = splits == 1 ? dW : part;
+    switch (K / 4) {
+      case 1: wgrad_thin_kernel<1><<<grid, 32, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+      case 2: wgrad_thin_kernel<2><<<grid, 64, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+      case 3: wgrad_thin_kernel<3><<<grid, 96, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+      case 4: wgrad_thin_kernel<4><<<grid, 128, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+      case 5: wgrad_thin_kernel<5><<<grid, 160, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+      case 6: wgrad_thin_kernel<6><<<grid, 192, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+      case 7: wgrad_thin_kernel<7><<<grid, 224, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+      default: wgrad_thin_kernel<8><<<grid, 256, 0, st>>>(A, lda, dH, ldh, dst, M, N, per); break;
+    }
+    GCS_CHECK_LAUNCH("wgrad_thin_kernel");
+    if (splits > 1) {
       int64_t blocks = ceil_div(kn, 256);
       if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
       split_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(part, splits, kn, dW);

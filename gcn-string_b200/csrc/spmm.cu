@@ -300,7 +300,7 @@ int g_spmm_mode = 0;   // 0 = auto, 1 = CSR row kernel, 2 = RB4 global-memory ke
 // Test / sweep hook (not part of the drop-in surface).
 extern "C" void gcs_debug_set_spmm_mode(int mode) { g_spmm_mode = mode; }
 namespace gcs { int spmm_mode() { return g_spmm_mode; } }
-namespace gcs { void slab_set_param(int id, int value); }
+namespace gcs { void slab_set_param(int id, int value); void set_thin_wgrad(int v); }
 namespace gcs { namespace tc { void set_wgrad_chain(int c); void set_max_chain_k(int k); void set_wgrad_pair(int v); void set_f16_mode(int v); void set_max_chain_k_f16(int k); void set_wgrad_f16(int v); } }
 extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 1 && value > 0) g_rows_iters = value;
@@ -311,6 +311,7 @@ extern "C" void gcs_debug_set_param(int id, int value) {
   if (id == 7) gcs::tc::set_f16_mode(value);             // 0 tf32 only, 1 fp16 inside the fused model, 2 fp16 everywhere
   if (id == 8) gcs::tc::set_max_chain_k_f16(value);
   if (id == 9) gcs::tc::set_wgrad_f16(value);                // 0 = weight gradient on the tf32 split only
+  if (id == 13) gcs::set_thin_wgrad(value);
   if (id == 10 || id == 11 || id == 12) gcs::slab_set_param(id, value);   // spmm_slab.cu: stages / stage bytes / grid
 }
 

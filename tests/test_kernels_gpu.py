@@ -226,6 +226,23 @@ def test_fp16_split_tensor_core_gemm(M, K, N, scaling):
         lib.gcs_debug_set_param(7, 1)
 
 
+@pytest.mark.parametrize("M,K,N", [(4096, 32, 256), (9001, 16, 256), (5003, 4, 64), (7000, 28, 200), (33333, 12, 512)])
+def test_linear_weight_gradient_thin_first_layer(M, K, N):
+    """dW of a thin layer (K <= 32: the first Dense of the pre-processing MLP, F = 16 in the reference's data, 32 in
+    BASELINE.json) runs on its own split-row FFMA kernel; against float64, on a strided dH view, and run-to-run
+    bit-identical (fixed summation order)."""
+    rng = np.random.default_rng(M + K)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    wide = rng.standard_normal((M, N + 8)).astype(np.float32)
+    dh = dev(wide)[:, 4:4 + N]
+    dw, db = ops.linear_bwd_weight(dev(a), dh)
+    ref = a.astype(np.float64).T @ wide[:, 4:4 + N].astype(np.float64)
+    assert rel_err(host(dw), ref) < TOL
+    assert rel_err(host(db), wide[:, 4:4 + N].astype(np.float64).sum(0)) < TOL
+    dw2, _ = ops.linear_bwd_weight(dev(a), dh)
+    assert torch.equal(dw, dw2)
+
+
 def test_linear_on_strided_views_of_the_concat_buffer():
     rng = np.random.default_rng(9)
     cat = dev(rng.standard_normal((500, 5 * 64)).astype(np.float32))
