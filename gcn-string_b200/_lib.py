@@ -22,7 +22,7 @@ class ModelConfig(Structure):
     _fields_ = [("in_features", c_int32), ("output", c_int32), ("hidden", c_int32),
                 ("message_passing", c_int32), ("pre_process", c_int32), ("post_process", c_int32),
                 ("connectivity", c_int32), ("pool", c_int32), ("final_activation", c_int32),
-                ("bn_momentum", c_float), ("bn_epsilon", c_float)]
+                ("bn_momentum", c_float), ("bn_epsilon", c_float), ("aggregate", c_int32)]
 
 
 class Batch(Structure):
@@ -30,7 +30,7 @@ class Batch(Structure):
                 ("rowptr", c_void_p), ("colidx", c_void_p), ("rowptr_t", c_void_p), ("colidx_t", c_void_p),
                 ("graph_ptr", c_void_p), ("x", c_void_p), ("ldx", c_int64), ("y", c_void_p),
                 ("seg_ids", c_void_p), ("rb4_blk_ptr", c_void_p), ("rb4_ent", c_void_p), ("rb4_blk_ptr_t", c_void_p), ("rb4_ent_t", c_void_p),
-                ("max_graph_nodes", c_int32), ("reserved", c_int32)]
+                ("max_graph_nodes", c_int32), ("reserved", c_int32), ("values", c_void_p), ("values_t", c_void_p)]
 
 
 P = c_void_p
@@ -71,6 +71,7 @@ PROTOTYPES = {
     "gcs_contact_map_fill": (c_int32, [P, P, I32, I64, ctypes.c_float, P, P, P, P]),
     "gcs_link_pairs_offsets": (c_int32, [P, I32, P, P, I32, P, P, P, I64, P]),
     "gcs_link_pairs": (c_int32, [P, P, P, P, P, I32, P, P, P, P, I64, P, P, P, P, I64, P]),
+    "gcs_spmm_aggregate_bwd": (c_int32, [P, P, P, P, P, P, I64, P, I64, I32, P, I64, P, P, P, P, I64, P, I64, P, I64, I32, P]),
     "gcs_spmm_aggregate": (c_int32, [P, P, P, P, P, I64, P, I64, P, P, P, P, I64, P, I64, I32, I32, P]),
     "gcs_segment_sum_fwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
     "gcs_segment_sum_bwd": (c_int32, [P, I64, P, I32, I32, P, I64, P]),
@@ -84,7 +85,7 @@ PROTOTYPES = {
     "gcs_comm_world_size": (c_int32, [P]),
     "gcs_allreduce_grads": (c_int32, [P, P, I64, P]),
     "gcs_allreduce_f64": (c_int32, [P, P, I64, P]),
-    "gcs_model_train_step_dp": (c_int32, [POINTER(ModelConfig), P, P, POINTER(Batch), F32, P, P, P, P, I64, P, P, P]),
+    "gcs_model_train_step_dp": (c_int32, [POINTER(ModelConfig), P, P, POINTER(Batch), F32, P, P, P, P, I64, P, P, P, I32]),
     "gcs_model_num_params": (c_int64, [POINTER(ModelConfig)]),
     "gcs_model_num_state": (c_int64, [POINTER(ModelConfig)]),
     "gcs_model_workspace_bytes": (c_int64, [POINTER(ModelConfig), I64, I64, I32, I32]),
@@ -165,11 +166,11 @@ def stream_ptr(stream=None) -> int:
 
 def model_config(cfg) -> ModelConfig:
     """params.GNNConfig -> C struct."""
-    from .params import CONNECTIVITY, FINAL_ACT, POOL
+    from .params import AGGREGATE, CONNECTIVITY, FINAL_ACT, POOL
     cfg.validate()
     return ModelConfig(cfg.in_features, cfg.output, cfg.hidden, cfg.message_passing, cfg.pre_process,
                        cfg.post_process, CONNECTIVITY[cfg.connectivity], POOL[cfg.pool],
-                       FINAL_ACT[cfg.activation], cfg.bn_momentum, cfg.bn_epsilon)
+                       FINAL_ACT[cfg.activation], cfg.bn_momentum, cfg.bn_epsilon, AGGREGATE[cfg.aggregate])
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int32, c_void_p, c_int64, c_void_p, c_void_p)

@@ -87,6 +87,11 @@ static int check_config(const gcs_model_config* c) {
   if (c->pool != 0 && c->pool != 1) return fail(GCS_ERR_UNSUPPORTED, "model config: pool must be 'sum' or None");
   if (c->final_activation != 0 && c->final_activation != 1)
     return fail(GCS_ERR_UNSUPPORTED, "model config: final activation must be linear or softmax");
+  if (c->aggregate < 0 || c->aggregate > 2)
+    return fail(GCS_ERR_INVALID_ARGUMENT, "model config: aggregate must be 0 ('sum'), 1 ('mean') or 2 ('max')");
+  if (c->aggregate == 2 && c->connectivity == 2)
+    return fail(GCS_ERR_UNSUPPORTED, "model config: aggregate='max' with connectivity='sum' is not built (the backward needs the "
+                                     "aggregation's own output, which the skip connection overwrites)");
   if (c->final_activation == 1 && c->output > 64)
     return fail(GCS_ERR_UNSUPPORTED, "model config: softmax over more than 64 classes is not built");
   return GCS_OK;
@@ -242,18 +247,37 @@ static int check_batch(const gcs_model_config& c, const gcs_batch* b, bool need_
     return fail(GCS_ERR_INVALID_ARGUMENT, "batch: the backward of the pool needs seg_ids (the batch index i)");
   if (need_transpose && (!b->rowptr_t || (b->nnz > 0 && !b->colidx_t)))
     return fail(GCS_ERR_INVALID_ARGUMENT, "batch: the backward needs the transposed CSR (alias it if symmetric)");
+  if (need_transpose && b->values && !b->values_t)
+    return fail(GCS_ERR_INVALID_ARGUMENT, "batch: the backward needs the edge weights in transposed order (values_t)");
   return GCS_OK;
 }
 
 // Y = pattern(A) . f(X) (+ residual) for the batch: per-graph shared-memory slabs when the batch says how long its graphs
 // are (gcs_spmm_sum_graphs), the global-memory kernels otherwise.  transposed selects pattern(A)^T (the backward).
 static int aggregate(const gcs_batch& bt, bool transposed, const float* X, int64_t ldx, const float* scale, const float* shift,
-                     const float* alpha, const float* residual, int64_t ldr, float* Y, int64_t ldy, int H, gcs_stream st) {
+                     const float* alpha, const float* residual, int64_t ldr, float* Y, int64_t ldy, int H, gcs_stream st,
+                     int agg = 0) {
+  if (agg != 0 || bt.values)                         // weighted / mean / max: the general row kernel
+    return gcs_spmm_aggregate(transposed ? bt.rowptr_t : bt.rowptr, transposed ? bt.colidx_t : bt.colidx,
+                              transposed ? bt.values_t : bt.values, nullptr, nullptr, bt.n_nodes, X, ldx, scale, shift, alpha,
+                              residual, ldr, Y, ldy, H, agg, st);
   const int height = bt.rb_height ? bt.rb_height : 4;
   return gcs_spmm_sum_graphs(bt.graph_ptr, bt.n_graphs, bt.max_graph_nodes, transposed ? bt.rowptr_t : bt.rowptr,
                              transposed ? bt.colidx_t : bt.colidx, transposed ? bt.rb4_blk_ptr_t : bt.rb4_blk_ptr,
                              transposed ? bt.rb4_ent_t : bt.rb4_ent, height, bt.n_nodes, X, ldx, scale, shift, alpha, residual,
                              ldr, Y, ldy, H, st);
+}
+
+// dLoss/d(a_k) from dz = dLoss/d(z_k), z_k = agg(a_k): the transposed aggregation.  Z: the forward output z_k (max only).
+static int aggregate_bwd(const gcs_model_config& c, const Plan& p, const gcs_batch& bt, int bi, const float* params,
+                         const float* dz, int64_t lddz, const float* Z, int64_t ldz, gcs_stream st) {
+  const int H = p.H;
+  if (c.aggregate == 0 && !bt.values)
+    return aggregate(bt, true, dz, lddz, nullptr, nullptr, nullptr, nullptr, 0, p.tmp_a, H, H, st);
+  const float* scale = p.stat[bi] + 2 * H;
+  return gcs_spmm_aggregate_bwd(bt.rowptr_t, bt.colidx_t, bt.values ? bt.values_t : nullptr, bt.rowptr, bt.colidx, bt.values,
+                                bt.n_nodes, dz, lddz, c.aggregate, p.h[bi], H, scale, scale + H, params + p.blocks[bi].alpha(), Z,
+                                ldz, p.tmp_b, H, p.tmp_a, H, H, st);
 }
 
 // BatchNorm statistics -> folded scale/shift for block bi over `rows` rows of h.
@@ -343,7 +367,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     }
     if (fused) {
       GCS_TIMED("spmm_fwd", aggregate(bt, false, p.h[bi], H, nullptr, nullptr, nullptr, c.connectivity == 2 ? emb(k) : nullptr, H,
-                                      emb(k + 1), ld_emb, H, st));
+                                      emb(k + 1), ld_emb, H, st, c.aggregate));
       continue;
     }
     int with_stats = 0;
@@ -356,7 +380,7 @@ static int run_forward(const gcs_model_config& c, const Plan& p, const float* pa
     GCS_TRY(block_norm(c, p, bi, params, state, p.h[bi], H, N, training, st, with_stats ? p.stat_part : nullptr));
     // z_k is the leading block of out_{k+1} ('cat'), or out_{k+1} = z_k (+ out_k for 'sum') in the next slab
     GCS_TIMED("spmm_fwd", aggregate(bt, false, p.h[bi], H, scale, scale + H, params + b.alpha(),
-                                    c.connectivity == 2 ? emb(k) : nullptr, H, emb(k + 1), ld_emb, H, st));
+                                    c.connectivity == 2 ? emb(k) : nullptr, H, emb(k + 1), ld_emb, H, st, c.aggregate));
   }
   // global sum pool
   amax_sink() = AmaxSink();                                 // pooled rows and the post-MLP: tf32 kernels / CUDA cores
@@ -494,7 +518,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
       dz = blk;
       lddz = Wc;
     }
-    GCS_TIMED("spmm_bwd", aggregate(bt, true, dz, lddz, nullptr, nullptr, nullptr, nullptr, 0, p.tmp_a, H, H, st));
+    GCS_TIMED("spmm_bwd", aggregate_bwd(c, p, bt, bi, params, dz, lddz, p.cat + static_cast<int64_t>(L - 1 - k) * H, Wc, st));
     GCS_TRY(block_backward(c, p, bi, params, grads, p.tmp_a, H, p.h[bi], H, N, p.cat + static_cast<int64_t>(L - k) * H, Wc,
                            p.dhcat + static_cast<int64_t>(k) * H, ldd, nullptr, 0, 0, st));
     if (k == L - 1 || k == (L - 1) / 2) GCS_TRY(notify(bi));   // two buckets inside the message-passing stack
@@ -515,7 +539,7 @@ static int run_backward(const gcs_model_config& c, const Plan& p, const float* p
       g = p.tmp_c;
     }
     for (int k = L - 1; k >= 0; --k) {
-      GCS_TIMED("spmm_bwd", aggregate(bt, true, g, H, nullptr, nullptr, nullptr, nullptr, 0, p.tmp_a, H, H, st));
+      GCS_TIMED("spmm_bwd", aggregate_bwd(c, p, bt, P + k, params, g, H, emb(k + 1), H, st));
       GCS_TRY(block_backward(c, p, P + k, params, grads, p.tmp_a, H, p.h[P + k], H, N, emb(k), ld_emb, p.dhcat, H, g, H,
                              c.connectivity == 2 ? 1 : 0, st));
       if (k == L - 1 || k == (L - 1) / 2) GCS_TRY(notify(P + k));
@@ -651,10 +675,24 @@ cudaEvent_t* dp_events() {           // per host thread: recorded and waited on 
 }
 }  // namespace
 
+namespace {
+int dp_sync_bn(double* buf, int64_t n, gcs_stream stream, void* user) {   // synchronised BatchNorm over the step's communicator
+  return gcs_allreduce_f64(static_cast<gcs_comm*>(user), buf, n, stream);
+}
+struct HookScope {                                                        // call-scoped: restored on every exit path
+  SyncHook saved;
+  bool active;
+  HookScope(gcs_comm* comm, bool on) : saved(sync_hook()), active(on) {
+    if (on) { sync_hook().fn = dp_sync_bn; sync_hook().user = comm; sync_hook().world = gcs_comm_world_size(comm); }
+  }
+  ~HookScope() { if (active) sync_hook() = saved; }
+};
+}  // namespace
+
 extern "C" int gcs_model_train_step_dp(const gcs_model_config* cfg, const float* params, float* state,
                                        const gcs_batch* batch, float grad_scale, float* grads, float* probs,
                                        float* loss_acc, void* workspace, int64_t workspace_bytes, gcs_stream stream,
-                                       gcs_comm* comm, gcs_stream comm_stream) {
+                                       gcs_comm* comm, gcs_stream comm_stream, int32_t sync_batchnorm) {
   GCS_TRY(check_config(cfg));
   GCS_TRY(check_batch(*cfg, batch, true, true));
   GCS_CHECK_ARG(cfg->final_activation == 1, "gcs_model_train_step_dp: the loss is categorical cross-entropy on a softmax output");
@@ -669,6 +707,7 @@ extern "C" int gcs_model_train_step_dp(const gcs_model_config* cfg, const float*
   if (workspace_bytes < total)
     return fail(GCS_ERR_WORKSPACE, "gcs_model_train_step_dp: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
   GCS_CHECK_ARG(p.rows_post < INT32_MAX, "gcs_model_train_step_dp: too many output rows");
+  HookScope hook(comm, sync_batchnorm != 0 && gcs_comm_world_size(comm) > 1);
   GCS_TRY(run_forward(c, p, params, state, bt, true, stream));
   GCS_TRY(gcs_softmax_xent(p.logits, bt.y, static_cast<int32_t>(p.rows_post), p.C, probs, loss_acc, p.dlogits, grad_scale, stream));
   cudaEvent_t* ev = dp_events();

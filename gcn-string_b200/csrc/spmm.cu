@@ -244,6 +244,86 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(
   amax_commit(mx, amax);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward of the general aggregation: given dZ = dLoss/dZ for Z = agg_j(w_ij * a[j]), a = f(h),
+// dA[j] = dLoss/da[j], gathered over the TRANSPOSED pattern (row j of A^T lists the rows i that have j as a neighbour;
+// values_t are the weights in that order):
+//   sum : dA[j] = sum_i w_ij * dZ[i]
+//   mean: dA[j] = sum_i w_ij * dZ[i] / deg_i            deg_i = entries of row i (scatter_mean divides by the count)
+//   max : dA[j, c] = sum_i [w_ij * a[j, c] == Z[i, c]] * w_ij * dZ[i, c] / ties[i, c]
+//         (tf.math.unsorted_segment_max's gradient: the maxima of a segment share its gradient equally; ties[i, c] is
+//         the number of neighbours of i that attain the maximum, counted by spmm_max_ties_kernel)
+// One owner thread per output element, entries in ascending column order: deterministic.
+template <int VEC>
+__global__ void __launch_bounds__(256) spmm_agg_bwd_kernel(
+    const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ colidx_t, const float* __restrict__ values_t,
+    int64_t n_rows, const float* __restrict__ dZ, int64_t lddz, int agg, const int32_t* __restrict__ fwd_rowptr,
+    const float* __restrict__ Z, int64_t ldz, const float* __restrict__ ties, int64_t ldt, const float* __restrict__ Hpre,
+    int64_t ldh, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha,
+    float* __restrict__ dA, int64_t ldda, int H, int lanes, int rows_per_block) {
+  const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+  const int c = lane * VEC;
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * rows_per_block + slot;
+  if (slot >= rows_per_block || j >= n_rows || c >= H) return;
+  float own[VEC], acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    acc[k] = 0.f;
+    own[k] = 0.f;
+    if (agg == kAggMax && c + k < H) {
+      const float x = __ldg(Hpre + j * ldh + c + k);
+      own[k] = scale ? bn_prelu(x, __ldg(scale + c + k), __ldg(shift + c + k), __ldg(alpha + c + k)) : x;
+    }
+  }
+  const int eb = __ldg(rowptr_t + j), ee = __ldg(rowptr_t + j + 1);
+  for (int e = eb; e < ee; ++e) {
+    const int64_t i = __ldg(colidx_t + e);
+    float w = values_t ? __ldg(values_t + e) : 1.f;
+    const float wv = w;
+    if (agg == kAggMean) w = w / static_cast<float>(__ldg(fwd_rowptr + i + 1) - __ldg(fwd_rowptr + i));
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      if (c + k >= H) continue;
+      const float g = __ldg(dZ + i * lddz + c + k);
+      if (agg == kAggMax) {
+        const float m = values_t ? own[k] * wv : own[k];
+        if (m == __ldg(Z + i * ldz + c + k)) acc[k] += (values_t ? g * wv : g) / __ldg(ties + i * ldt + c + k);
+      } else {
+        acc[k] += values_t || agg == kAggMean ? g * w : g;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k)
+    if (c + k < H) dA[j * ldda + c + k] = acc[k];
+}
+
+// ties[i, c] = number of entries (i, j) with w_ij * f(h[j, c]) == Z[i, c]  (forward pattern; >= 1 for a non-empty row)
+__global__ void __launch_bounds__(256) spmm_max_ties_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ values, int64_t n_rows,
+    const float* __restrict__ Hpre, int64_t ldh, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ alpha, const float* __restrict__ Z, int64_t ldz, float* __restrict__ ties, int64_t ldt, int H,
+    int rows_per_block) {
+  const int lanes = H < 256 ? H : 256;
+  const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * rows_per_block + slot;
+  if (slot >= rows_per_block || i >= n_rows) return;
+  const int eb = __ldg(rowptr + i), ee = __ldg(rowptr + i + 1);
+  for (int c = lane; c < H; c += lanes) {
+    const float z = __ldg(Z + i * ldz + c);
+    const float sc = scale ? __ldg(scale + c) : 1.f, sh = scale ? __ldg(shift + c) : 0.f, al = scale ? __ldg(alpha + c) : 1.f;
+    int n = 0;
+    for (int e = eb; e < ee; ++e) {
+      const int64_t j = __ldg(colidx + e);
+      const float x = __ldg(Hpre + j * ldh + c);
+      const float a = scale ? bn_prelu(x, sc, sh, al) : x;
+      n += (values ? a * __ldg(values + e) : a) == z;
+    }
+    ties[i * ldt + c] = static_cast<float>(n > 0 ? n : 1);
+  }
+}
+
+
 }  // namespace gcs
 
 using namespace gcs;
@@ -393,3 +473,46 @@ extern "C" int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const 
   return gcs_spmm_aggregate(rowptr, colidx, nullptr, rb4_blk_ptr, rb4_ent, n_rows, X, ldx, scale, shift, alpha, nullptr, 0,
                             Y, ldy, H, kAggSum, stream);
 }
+
+// Backward of gcs_spmm_aggregate with respect to f(X) (see spmm_agg_bwd_kernel).  (rowptr_t, colidx_t, values_t): the
+// TRANSPOSED pattern with its weights in that order; fwd_rowptr: the forward row pointers (mean: entry counts);
+// max additionally needs the forward inputs again: (rowptr, colidx, values) forward pattern, X (pre-prologue, with
+// scale / shift / alpha as in the forward) and the forward output Z; `ties` [n_rows, H] is scratch.
+extern "C" int gcs_spmm_aggregate_bwd(const int32_t* rowptr_t, const int32_t* colidx_t, const float* values_t,
+                                      const int32_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows,
+                                      const float* dZ, int64_t lddz, int32_t aggregate, const float* X, int64_t ldx,
+                                      const float* scale, const float* shift, const float* alpha, const float* Z, int64_t ldz,
+                                      float* ties, int64_t ldt, float* dA, int64_t ldda, int32_t H, gcs_stream stream) {
+  GCS_CHECK_ARG(n_rows >= 0 && H > 0, "gcs_spmm_aggregate_bwd: bad size");
+  GCS_CHECK_ARG(aggregate == kAggSum || aggregate == kAggMean || aggregate == kAggMax, "gcs_spmm_aggregate_bwd: aggregate must be 0, 1 or 2");
+  if (n_rows == 0) return GCS_OK;
+  GCS_CHECK_ARG(rowptr_t && colidx_t && dZ && dA && lddz >= H && ldda >= H, "gcs_spmm_aggregate_bwd: bad pointer / leading dimension");
+  GCS_CHECK_ARG(aggregate != kAggMean || rowptr, "gcs_spmm_aggregate_bwd: mean needs the forward row pointers");
+  GCS_CHECK_ARG(aggregate != kAggMax || (rowptr && colidx && X && Z && ties && ldx >= H && ldz >= H && ldt >= H),
+                "gcs_spmm_aggregate_bwd: max needs the forward pattern, X, Z and the ties scratch");
+  GCS_CHECK_ARG((scale != nullptr) == (shift != nullptr) && (scale != nullptr) == (alpha != nullptr),
+                "gcs_spmm_aggregate_bwd: scale/shift/alpha must be all NULL or all set");
+  GCS_CHECK_ARG(n_rows < INT32_MAX, "gcs_spmm_aggregate_bwd: n_rows exceeds int32 CSR range");
+  cudaStream_t st = as_stream(stream);
+  if (aggregate == kAggMax) {
+    const int lanes = H < 256 ? H : 256;
+    const int rpb = 256 / lanes;
+    spmm_max_ties_kernel<<<static_cast<unsigned>(ceil_div(n_rows, rpb)), 256, 0, st>>>(rowptr, colidx, values, n_rows, X, ldx, scale,
+                                                                                      shift, alpha, Z, ldz, ties, ldt, H, rpb);
+    GCS_CHECK_LAUNCH("spmm_max_ties_kernel");
+  }
+  if (H <= 256) {
+    const int rpb = 256 / H;
+    spmm_agg_bwd_kernel<1><<<static_cast<unsigned>(ceil_div(n_rows, rpb)), 256, 0, st>>>(
+        rowptr_t, colidx_t, values_t, n_rows, dZ, lddz, aggregate, rowptr, Z, ldz, ties, ldt, X, ldx, scale, shift, alpha, dA, ldda, H, H, rpb);
+  } else {
+    const int lanes = (H + 3) / 4;
+    GCS_CHECK_ARG(lanes <= 256, "gcs_spmm_aggregate_bwd: H too wide");
+    const int rpb = 256 / lanes;
+    spmm_agg_bwd_kernel<4><<<static_cast<unsigned>(ceil_div(n_rows, rpb)), 256, 0, st>>>(
+        rowptr_t, colidx_t, values_t, n_rows, dZ, lddz, aggregate, rowptr, Z, ldz, ties, ldt, X, ldx, scale, shift, alpha, dA, ldda, H, lanes, rpb);
+  }
+  GCS_CHECK_LAUNCH("spmm_agg_bwd_kernel");
+  return GCS_OK;
+}
+

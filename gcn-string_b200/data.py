@@ -123,6 +123,8 @@ class SparseAdjacency:
         self._t = None
         self._rb = {}
         self._rb_t = {}
+        self.edge_weight = None        # optional float32 [nnz] in CSR order; read only by GeneralGNN(use_edge_weights=True)
+        self._edge_weight_t = None
 
     @classmethod
     def from_indices(cls, indices, dense_shape, values=None):
@@ -199,6 +201,18 @@ class SparseAdjacency:
         """Block height the model entry points are given: 4 rows per block is the faster format at every width and
         degree of the cfg4 sweep (profiles/r02_cfg4_spmm_sweep.jsonl; 2 rows per block only ties at degree 4)."""
         return 4
+
+    def edge_weight_t(self):
+        """The edge weights in the entry order of the transposed pattern (columns ascending, then rows)."""
+        if self.edge_weight is None:
+            return None
+        if self._edge_weight_t is None or self._edge_weight_t[0] is not self.edge_weight:
+            torch = _lib.require_cuda()
+            counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+            rows = torch.repeat_interleave(torch.arange(self.n_rows, device="cuda"), counts)
+            key = self.colidx.to(torch.int64) * self.n_rows + rows
+            self._edge_weight_t = (self.edge_weight, self.edge_weight[torch.argsort(key)].contiguous())
+        return self._edge_weight_t[1]
 
     def transposed(self):
         """(rowptr_t, colidx_t) of pattern(A)^T; the same arrays when symmetric."""

@@ -179,8 +179,12 @@ class DataParallelTrainer:
         a = inputs[1]
         if global_batch is None:
             global_batch = getattr(a, "global_batch_graphs", None) or target.shape[0] * ws
-        step = lambda: self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch), comm=self.comm)   # noqa: E731
-        loss_acc, probs = self._hooked(step)
+        if self.comm is not None:                 # the library's own communicator: collectives (and synchronised BatchNorm) per call
+            loss_acc, probs = self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch), comm=self.comm,
+                                                          sync_bn=self.sync_bn)
+        else:
+            step = lambda: self.model.train_step_grads(inputs, target, grad_scale=1.0 / float(global_batch))   # noqa: E731
+            loss_acc, probs = self._hooked(step)
         if self.comm is None:
             allreduce_gradients(self.model.grads, self.group)
         self.optimizer.apply_flat(self.model.params, self.model.grads)

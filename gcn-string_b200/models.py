@@ -91,7 +91,7 @@ class Variable:
 class GeneralGNN:
     def __init__(self, output, activation=None, hidden=256, message_passing=4, pre_process=2, post_process=2,
                  connectivity="cat", batch_norm=True, dropout=0.0, aggregate="sum", hidden_activation="prelu",
-                 pool="sum", seed: Optional[int] = None):
+                 pool="sum", seed: Optional[int] = None, use_edge_weights: bool = False):
         self.config = dict(output=output, activation=activation, hidden=hidden, message_passing=message_passing,
                            pre_process=pre_process, post_process=post_process, connectivity=connectivity,
                            batch_norm=batch_norm, dropout=dropout, aggregate=aggregate,
@@ -99,6 +99,9 @@ class GeneralGNN:
         # validate everything that does not depend on the input width now (no silent fallback)
         GNNConfig(in_features=1, **self.config).validate()
         self.seed = seed
+        # GeneralConv ignores adjacency values; the reference's `use_edge_data` switch (gcn.py:73-80)
+        # wanted them: with use_edge_weights=True the aggregation weights every message by a.edge_weight[entry]
+        self.use_edge_weights = bool(use_edge_weights)
         self.built = False
         self.losses: List = []          # no regularisers (gcn.py:335 adds sum(model.losses) == 0)
         self.cfg: Optional[GNNConfig] = None
@@ -221,10 +224,18 @@ class GeneralGNN:
         rb4 = a.rb(height) if use_rb4 else (None, None)
         rb4_t = a.rb_t(height) if (use_rb4 and need_transpose) else (None, None)   # the same arrays when the pattern is symmetric
         max_nodes = a.max_graph_nodes if a.graph_ptr is not None else (x.shape[0] if n_graphs == 1 else 0)
+        ew, ew_t = None, None
+        if self.use_edge_weights:
+            if getattr(a, "edge_weight", None) is None:
+                raise ValueError("use_edge_weights=True but the adjacency carries no edge_weight")
+            a.edge_weight = a.edge_weight.to(device="cuda", dtype=torch.float32).contiguous()
+            if a.edge_weight.shape[0] != a.nnz:
+                raise ValueError("edge_weight must hold one value per stored entry (CSR order)")
+            ew, ew_t = a.edge_weight, (a.edge_weight_t() if need_transpose else None)
         batch = _lib.Batch(x.shape[0], a.nnz, n_graphs, height, ptr(a.rowptr), ptr(a.colidx), ptr(rp_t), ptr(ci_t),
                            ptr(graph_ptr), ptr(x), x.stride(0) if x.shape[0] > 1 else x.shape[1], None,
-                           ptr(seg), ptr(rb4[0]), ptr(rb4[1]), ptr(rb4_t[0]), ptr(rb4_t[1]), int(max_nodes), 0)
-        keep = (x, a, graph_ptr, rp_t, ci_t, rb4, rb4_t, seg)   # keep device buffers alive
+                           ptr(seg), ptr(rb4[0]), ptr(rb4[1]), ptr(rb4_t[0]), ptr(rb4_t[1]), int(max_nodes), 0, ptr(ew), ptr(ew_t))
+        keep = (x, a, graph_ptr, rp_t, ci_t, rb4, rb4_t, seg, ew, ew_t)   # keep device buffers alive
         return batch, keep
 
     def _workspace(self, batch, training):
@@ -267,7 +278,7 @@ class GeneralGNN:
         check(lib.gcs_model_backward(self._c, ptr(self.params), ctx["batch"], ptr(dlogits), ptr(self.grads),
                                      ptr(ctx["ws"]), ctx["ws"].numel(), stream_ptr()), "gcs_model_backward")
 
-    def train_step_grads(self, inputs, target, grad_scale: Optional[float] = None, comm=None):
+    def train_step_grads(self, inputs, target, grad_scale: Optional[float] = None, comm=None, sync_bn: bool = False):
         """Fused training-mode forward + categorical cross-entropy + backward (one C call).
         Leaves the gradients in ``self.grads``; returns (loss_acc [2] device tensor = {loss,
         accuracy}, probs [B, C]).  ``grad_scale`` defaults to 1/B (mean loss, gcn.py:335).
@@ -290,7 +301,7 @@ class GeneralGNN:
         if comm is not None:
             check(lib.gcs_model_train_step_dp(self._c, ptr(self.params), ptr(self.state), batch, gs, ptr(self.grads),
                                               ptr(probs), ptr(loss_acc), ptr(ws), ws.numel(), stream_ptr(), comm.handle,
-                                              comm.stream.cuda_stream), "gcs_model_train_step_dp")
+                                              comm.stream.cuda_stream, int(bool(sync_bn))), "gcs_model_train_step_dp")
         else:
             check(lib.gcs_model_train_step(self._c, ptr(self.params), ptr(self.state), batch, gs, ptr(self.grads),
                                            ptr(probs), ptr(loss_acc), ptr(ws), ws.numel(), stream_ptr()),

@@ -22,6 +22,7 @@ from typing import List, Optional, Tuple
 CONNECTIVITY = {None: 0, "cat": 1, "sum": 2}
 POOL = {None: 0, "sum": 1}
 FINAL_ACT = {None: 0, "linear": 0, "softmax": 1}
+AGGREGATE = {"sum": 0, "mean": 1, "max": 2}          # spektral scatter_sum / scatter_mean / scatter_max
 
 
 @dataclass(frozen=True)
@@ -45,8 +46,10 @@ class GNNConfig:
 
     def validate(self) -> None:
         """Raise for anything outside the native subset (no fallback)."""
-        if self.aggregate != "sum":
-            raise NotImplementedError("native path implements aggregate='sum' only")
+        if self.aggregate not in AGGREGATE:
+            raise NotImplementedError("native path implements aggregate in {'sum', 'mean', 'max'}")
+        if self.aggregate == "max" and self.connectivity == "sum":
+            raise NotImplementedError("aggregate='max' with connectivity='sum' is not built")
         if self.pool not in POOL:
             raise NotImplementedError("native path implements pool in {'sum', None}")
         if self.connectivity not in CONNECTIVITY:

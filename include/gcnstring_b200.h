@@ -222,6 +222,17 @@ int gcs_spmm_aggregate(const int32_t* rowptr, const int32_t* colidx, const float
                        const float* residual, int64_t ldr, float* Y, int64_t ldy, int32_t H,
                        int32_t aggregate, gcs_stream stream);
 
+/* Gradient of gcs_spmm_aggregate with respect to f(X): dA[j] = sum_i w_ij * dZ[i] (sum), / (entries of row i) (mean),
+ * or - max - only where w_ij * f(X[j]) attains the maximum Z[i], shared equally between ties (the gradient of
+ * tf.math.unsorted_segment_max).  (rowptr_t, colidx_t, values_t): the transposed pattern with the weights in that order
+ * (alias the forward arrays for a symmetric matrix with symmetric weights).  mean also reads the forward rowptr; max also
+ * reads the forward pattern + weights, X with its prologue, the forward output Z, and uses ties[n_rows, H] as scratch. */
+int gcs_spmm_aggregate_bwd(const int32_t* rowptr_t, const int32_t* colidx_t, const float* values_t,
+                           const int32_t* rowptr, const int32_t* colidx, const float* values, int64_t n_rows,
+                           const float* dZ, int64_t lddz, int32_t aggregate, const float* X, int64_t ldx,
+                           const float* scale, const float* shift, const float* alpha, const float* Z, int64_t ldz,
+                           float* ties, int64_t ldt, float* dA, int64_t ldda, int32_t H, gcs_stream stream);
+
 /* ---------------------------------------------------------------------------------
  * K4/K6  GlobalSumPool = tf.math.segment_sum(X, i) over sorted graph ids, and its
  * gradient dX[n] = dOut[i[n]].
@@ -318,6 +329,7 @@ typedef struct gcs_model_config {
   int32_t final_activation; /* 0 = linear, 1 = softmax */
   float bn_momentum;        /* 0.99 */
   float bn_epsilon;         /* 1e-3 */
+  int32_t aggregate;        /* GeneralConv aggregate: 0 = 'sum' (the reference's), 1 = 'mean', 2 = 'max' */
 } gcs_model_config;
 
 typedef struct gcs_batch {
@@ -340,6 +352,9 @@ typedef struct gcs_batch {
   const uint32_t* rb4_ent_t;
   int32_t max_graph_nodes;      /* longest graph of the batch (host-known), 0 = unknown: selects the shared-memory slab */
   int32_t reserved;             /*   aggregation kernel (gcs_spmm_sum_graphs) when graph_ptr is set */
+  const float* values;          /* optional per-entry weights w_ij in CSR order (the `use_edge_data` switch of gcn.py:73-80);
+                                   NULL = pattern only, as GeneralConv aggregates */
+  const float* values_t;        /* the same weights in the order of (rowptr_t, colidx_t); backward only */
 } gcs_batch;
 
 /* Number of floats in the flat trainable / state buffers (layout: gcn-string_b200/params.py). */
@@ -365,11 +380,13 @@ int gcs_model_train_step(const gcs_model_config* cfg, const float* params, float
  * all-reduce of `grads` over `comm`, issued on comm_stream in three buckets as the backward finishes trailing ranges of
  * the flat gradient buffer (post-MLP + last GeneralConv layers first), so that the reduction of all but the last bucket
  * overlaps the rest of the backward.  `stream` is made to wait for the reductions before anything enqueued after this
- * call (the optimizer step) runs. */
+ * call (the optimizer step) runs.  sync_batchnorm != 0: the BatchNorm statistics of this call are all-reduced over
+ * `comm` as well (fp64 sums, on `stream`) - the step then equals ONE single-device step on the union of the shards;
+ * no hook needs to be installed for that (the library's state is per call). */
 int gcs_model_train_step_dp(const gcs_model_config* cfg, const float* params, float* state,
                             const gcs_batch* batch, float grad_scale, float* grads, float* probs,
                             float* loss_acc, void* workspace, int64_t workspace_bytes, gcs_stream stream,
-                            gcs_comm* comm, gcs_stream comm_stream);
+                            gcs_comm* comm, gcs_stream comm_stream, int32_t sync_batchnorm);
 
 /* Split form of the train step, for callers that compute the loss themselves (the
  * GradientTape pattern of gcn.py:333-337): gcs_model_forward(training=1) leaves the

@@ -95,14 +95,53 @@ def spmm_sum(rows, cols, x, n):
     return out
 
 
+def aggregate(rows, cols, x, n, agg="sum", w=None):
+    """spektral.layers.ops scatter_sum / scatter_mean / scatter_max over messages w_ij * x[j]:
+    tf.math.unsorted_segment_{sum,mean,max}(messages, targets, n).  An empty row gives 0 (sum, mean) or the lowest
+    float (max).  Returns (out, ctx) with what the gradient needs."""
+    msg = x[cols] if w is None else x[cols] * w[:, None]
+    if agg == "sum":
+        out = np.zeros((n, x.shape[1]), dtype=x.dtype)
+        np.add.at(out, rows, msg)
+        return out, None
+    cnt = np.bincount(rows, minlength=n).astype(x.dtype)
+    if agg == "mean":
+        out = np.zeros((n, x.shape[1]), dtype=x.dtype)
+        np.add.at(out, rows, msg)
+        return out / np.maximum(cnt, 1.0)[:, None], cnt
+    assert agg == "max"
+    out = np.full((n, x.shape[1]), np.finfo(np.float32).min, dtype=x.dtype)
+    np.maximum.at(out, rows, msg)
+    return out, msg
+
+
+def aggregate_bwd(rows, cols, dz, n, agg="sum", w=None, ctx=None, z=None):
+    """Gradient of ``aggregate`` with respect to x.  max: tf's _UnsortedSegmentMinOrMaxGrad - the entries that attain a
+    row's maximum share its gradient equally."""
+    g = dz[rows]
+    if agg == "mean":
+        g = g / np.maximum(ctx, 1.0)[rows][:, None]
+    if agg == "max":
+        sel = (ctx == z[rows]).astype(dz.dtype)
+        num = np.zeros_like(dz)
+        np.add.at(num, rows, sel)
+        g = sel * g / np.maximum(num, 1.0)[rows]
+    if w is not None:
+        g = g * w[:, None]
+    out = np.zeros((n, dz.shape[1]), dtype=dz.dtype)
+    np.add.at(out, cols, g)
+    return out
+
+
 def segment_sum(x, seg, n_seg):
     out = np.zeros((n_seg, x.shape[1]), dtype=x.dtype)
     np.add.at(out, seg, x)
     return out
 
 
-def forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=False):
-    """Returns (output [B,C] (probabilities if activation == 'softmax'), cache)."""
+def forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=False, edge_weight=None):
+    """Returns (output [B,C] (probabilities if activation == 'softmax'), cache).  ``edge_weight``: optional per-entry
+    weights (the reference's unfinished ``use_edge_data`` switch); GeneralConv itself ignores adjacency values."""
     blocks = [Block(sp_, w, s) for sp_ in specs]
     P, L = cfg.pre_process, cfg.message_passing
     n = x.shape[0]
@@ -114,7 +153,9 @@ def forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=False):
     for blk in blocks[P:P + L]:
         a, c = _block_fwd(blk, out, training, cfg.bn_epsilon)
         caches.append(c)
-        z = spmm_sum(rows, cols, a, n)
+        ew = None if edge_weight is None else np.asarray(edge_weight, dtype=np.float64)
+        z, c["agg_ctx"] = aggregate(rows, cols, a, n, getattr(cfg, "aggregate", "sum"), ew)
+        c["agg_out"] = z
         # Concatenate()([z, out]) | Add()([z, out]) | no skip connection (GeneralGNN.call)
         out = np.concatenate([z, out], axis=1) if cfg.connectivity == "cat" else (z + out if cfg.connectivity == "sum" else z)
     node_out = out
@@ -141,7 +182,7 @@ def accuracy(probs, y):
     return float((probs.argmax(1) == y.argmax(1)).mean())
 
 
-def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs, prelu_branch=None):
+def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs, prelu_branch=None, edge_weight=None):
     """One training-mode forward + backward.  Returns dict(loss, acc, probs, grads (flat
     float64, same layout as w), new_state (flat float64 moving statistics)).
 
@@ -152,7 +193,7 @@ def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs, prelu_bran
     counts the elements whose pinned branch differs from the float64 sign."""
     assert cfg.activation == "softmax" and cfg.pool == "sum" and cfg.connectivity in ("cat", "sum", None)
     y = y.astype(np.float64)
-    probs, ctx = forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=True)
+    probs, ctx = forward(cfg, specs, w, s, x, rows, cols, seg, n_graphs, training=True, edge_weight=edge_weight)
     blocks, caches, logits = ctx["blocks"], ctx["caches"], ctx["logits"]
     loss, _ = xent_from_logits(logits, y)
     B = logits.shape[0]
@@ -174,7 +215,9 @@ def loss_and_grads(cfg, specs, w, s, x, rows, cols, seg, y, n_graphs, prelu_bran
             dz, dprev = dout[:, :H], dout[:, H:]
         else:                                           # Add: the gradient reaches both operands; None: only z
             dz, dprev = dout, (dout if cfg.connectivity == "sum" else 0.0)
-        da = spmm_sum(cols, rows, dz, x.shape[0])       # pattern(A)^T . dz
+        ew = None if edge_weight is None else np.asarray(edge_weight, dtype=np.float64)
+        da = aggregate_bwd(rows, cols, dz, x.shape[0], getattr(cfg, "aggregate", "sum"), ew, caches[bi]["agg_ctx"],
+                           caches[bi]["agg_out"])      # (sum, no weights: pattern(A)^T . dz)
         dout = dprev + _block_bwd(blocks[bi], caches[bi], da, grads, branch=br[bi])
     for bi in range(P - 1, -1, -1):
         dout = _block_bwd(blocks[bi], caches[bi], dout, grads, need_dx=bi > 0, branch=br[bi])

@@ -273,6 +273,53 @@ def test_node_level_output_without_pooling(small_case):
     assert out.shape == (n, 3) and rel_err(host(out), ref) < TOL
 
 
+@pytest.mark.parametrize("aggregate,weights,connectivity,hidden", [
+    ("mean", None, "cat", 16), ("max", None, "cat", 16), ("sum", "sym", "cat", 16), ("mean", "asym", None, 16),
+    ("max", "asym", None, 16), ("sum", "asym", "sum", 16), ("mean", "sym", "cat", 128), ("max", None, "cat", 128)])
+def test_weighted_mean_max_aggregation_train_step(small_case, aggregate, weights, connectivity, hidden):
+    """GeneralGNN(aggregate='mean' | 'max') and per-entry edge weights (use_edge_weights=True; the reference's
+    `use_edge_data` switch, gcn.py:73-80) inside the fused train step: loss, probabilities, BatchNorm state and every
+    gradient against the float64 oracle (max: the gradient of a row goes to the entries that attain its maximum, shared
+    between ties), and inference."""
+    c = small_case
+    cfg = GNNConfig(in_features=12, output=2, activation="softmax", hidden=hidden, message_passing=3, connectivity=connectivity,
+                    aggregate=aggregate)
+    specs = block_specs(cfg)
+    w, s = g.init_params(cfg, seed=14, perturb=True)
+    rows, cols = c["idx"][:, 0], c["idx"][:, 1]
+    rng = np.random.default_rng(3)
+    ew = None
+    if weights == "asym":
+        ew = rng.uniform(0.2, 1.5, rows.shape[0]).astype(np.float32)
+    elif weights == "sym":                                # w_ij = w_ji on the (symmetric) synthetic graphs
+        lo, hi = np.minimum(rows, cols), np.maximum(rows, cols)
+        ew = (0.3 + ((lo * 7919 + hi * 104729) % 1000) / 800.0).astype(np.float32)
+    args = (cfg, specs, w, s, c["x"], rows, cols, c["seg"], c["y"], 8)
+    ref = O1.loss_and_grads(*args, edge_weight=ew)
+    (x, a, i), y = next(g.DisjointLoader(c["ds"], batch_size=8, epochs=1, shuffle=False))
+    if ew is not None:
+        a.edge_weight = torch.from_numpy(ew).cuda()
+    kw = dict(hidden=hidden, message_passing=3, connectivity=connectivity, aggregate=aggregate, use_edge_weights=ew is not None)
+    model = g.GeneralGNN(2, activation="softmax", **kw)
+    model.build(12)
+    model.load_flat(w, s)
+    loss_acc, probs = model.train_step_grads([x, a, i], y)
+    assert abs(host(loss_acc)[0] - ref["loss"]) < TOL * abs(ref["loss"])
+    assert rel_err(host(probs), ref["probs"]) < TOL
+    assert rel_err(host(model.state), ref["new_state"]) < TOL
+    assert_grads_close(host(model.grads), ref["grads"], cfg, None, tol=2 * TOL)
+    g1 = model.grads.clone()
+    model.load_flat(w, s)
+    model.train_step_grads([x, a, i], y)
+    assert torch.equal(g1, model.grads)                       # deterministic
+    model.load_flat(w, s)
+    p_inf, _ = O1.forward(cfg, specs, w, s, c["x"], rows, cols, c["seg"], 8, False, edge_weight=ew)
+    assert rel_err(host(model([x, a, i], training=False)), p_inf) < TOL
+    if ew is None:
+        with pytest.raises(ValueError, match="edge_weight"):
+            g.GeneralGNN(2, activation="softmax", use_edge_weights=True, **{k: v for k, v in kw.items() if k != "use_edge_weights"})([x, a, i])
+
+
 @pytest.mark.parametrize("connectivity", ["sum", None])
 @pytest.mark.parametrize("hidden", [16, 128])
 def test_skip_connection_variants(small_case, connectivity, hidden):

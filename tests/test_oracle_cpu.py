@@ -37,7 +37,7 @@ def test_layout_is_dense_and_ordered():
     assert [b.has_alpha for b in block_specs(cfg)][-1] is False
 
 
-@pytest.mark.parametrize("kw", [dict(aggregate="mean"), dict(dropout=0.5), dict(hidden_activation="relu"),
+@pytest.mark.parametrize("kw", [dict(aggregate="prod"), dict(aggregate="max", connectivity="sum"), dict(dropout=0.5), dict(hidden_activation="relu"),
                                 dict(pool="max"), dict(batch_norm=False)])
 def test_unsupported_configurations_raise(kw):
     with pytest.raises(NotImplementedError):
@@ -159,6 +159,34 @@ def test_skip_connection_variants_in_both_restatements(small_case, connectivity)
     # the three variants are different functions of the same inputs
     cat = GNNConfig(in_features=12, output=2, activation="softmax", hidden=16, message_passing=3)
     assert n_trainable(cat) > n_trainable(cfg)
+
+
+@pytest.mark.parametrize("aggregate,weighted,connectivity", [("mean", False, "cat"), ("max", False, "cat"), ("sum", True, "cat"),
+                                                           ("mean", True, None), ("max", True, None), ("sum", True, "sum")])
+def test_general_aggregation_backward_matches_finite_differences(small_case, aggregate, weighted, connectivity):
+    """scatter_mean / scatter_max and per-entry weights in the oracle: the hand-derived backward -
+    max shares a row's gradient between the entries that attain the maximum, like tf's unsorted_segment_max gradient -
+    against central finite differences of the float64 forward."""
+    c = small_case
+    cfg = GNNConfig(in_features=12, output=2, activation="softmax", hidden=16, message_passing=2, connectivity=connectivity,
+                    aggregate=aggregate)
+    specs = block_specs(cfg)
+    w, s = g.init_params(cfg, seed=21, perturb=True)
+    rows, cols = c["idx"][:, 0], c["idx"][:, 1]
+    ew = np.random.default_rng(4).uniform(0.2, 1.5, rows.shape[0]) if weighted else None
+    r = O1.loss_and_grads(cfg, specs, w, s, c["x"], rows, cols, c["seg"], c["y"], 8, edge_weight=ew)
+
+    def loss_at(wv):
+        _, ctx = O1.forward(cfg, specs, wv, s, c["x"], rows, cols, c["seg"], 8, training=True, edge_weight=ew)
+        return O1.xent_from_logits(ctx["logits"], c["y"].astype(np.float64))[0]
+
+    scale = np.abs(r["grads"]).max()
+    for j in np.random.default_rng(8).integers(0, w.shape[0], 10):
+        wp = w.astype(np.float64).copy()
+        wm = wp.copy()
+        wp[j] += 1e-6
+        wm[j] -= 1e-6
+        assert abs((loss_at(wp) - loss_at(wm)) / 2e-6 - r["grads"][j]) < 2e-6 * scale + 1e-9
 
 
 def test_inference_uses_moving_statistics(small_case):
