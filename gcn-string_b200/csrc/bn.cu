@@ -132,17 +132,21 @@ __global__ void __launch_bounds__(256) bn_stats_final_kernel(const double* __res
 }
 
 // Statistics out of the dense layer's own epilogue (linear_tc.cu writes, per group of 32 rows and per column, the fp32
-// pair {sum h, sum h^2}): fold the groups into the same per-split fp64 partials the pass over h would have produced.
+// pair {group mean, sum of squared deviations from it}): fold the groups into the same per-split fp64 partials
+// {sum h, sum h^2} the pass over h would have produced - sum h = sum n_g*mean_g, sum h^2 = sum (M2_g + n_g*mean_g^2),
+// all in fp64, so that the only subtraction of large squares (E[h^2] - mean^2 in bn_stats_finish) happens in fp64.
 __global__ void __launch_bounds__(256) bn_stats_from_part_kernel(const float2* __restrict__ part, int64_t groups, int C,
-                                                                 int splits, double* __restrict__ ws) {
+                                                                 int splits, double* __restrict__ ws, int64_t M) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double acc[2] = {0.0, 0.0};
   if (c < C) {
     for (int64_t g = static_cast<int64_t>(blockIdx.y) * 8 + warp; g < groups; g += 8LL * splits) {
       const float2 v = __ldg(part + g * C + c);
-      acc[0] += static_cast<double>(v.x);
-      acc[1] += static_cast<double>(v.y);
+      const double n = static_cast<double>(M - g * 32 < 32 ? M - g * 32 : 32);
+      const double mg = static_cast<double>(v.x);
+      acc[0] += n * mg;
+      acc[1] += static_cast<double>(v.y) + n * mg * mg;
     }
   }
   block_store_partials<2>(acc, ws + (static_cast<int64_t>(blockIdx.y) * C + c) * 2, 0, 0, c < C);
@@ -544,7 +548,7 @@ int bn_stats_from_partials(const float* part, int64_t M, int C, float* mean, flo
   double* ws = static_cast<double*>(workspace);
   dim3 grid(static_cast<unsigned>(ceil_div(C, 32)), static_cast<unsigned>(splits));
   bn_stats_from_part_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(part), groups, C,
-                                                                static_cast<int>(splits), ws);
+                                                                static_cast<int>(splits), ws, M);
   GCS_CHECK_LAUNCH("bn_stats_from_part_kernel");
   return bn_stats_finish(ws, static_cast<int>(splits), C, M, mean, var, workspace, stream);
 }

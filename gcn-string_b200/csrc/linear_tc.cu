@@ -509,23 +509,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16 ? kHThreads : k
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        // BatchNorm statistics of the layer's output without another pass over it: lane c sums column c of the staged
-        // box (its 32 rows; rows past M excluded) - {sum, sum of squares} per 32-row group and column, fp32, folded in
-        // fp64 by bn_stats_from_partials.  The swizzled box is read conflict-free (one 128 B row per step).
+        // BatchNorm statistics of the layer's output without another pass over it: lane c reduces column c of the staged
+        // box (its 32 rows; rows past M excluded) to {group mean, sum of squared deviations from it}.  The sums are taken
+        // relative to the column's first row of the group (a pivot within one standard deviation or so of the values), so
+        // no large squares are subtracted from each other anywhere: Keras' two-pass variance is reproduced to fp32
+        // rounding also when |mean| >> std.  bn_stats_from_partials combines the groups in fp64 (mean_g, M2_g, n_g).
+        // The swizzled box is read conflict-free (one 128 B row per step).
         const int64_t grow = m0 + quarter * 32;
         if (stats_part && grow < M) {
-          float ssum = 0.f, ssq = 0.f;
+          float ssum = 0.f, ssq = 0.f, pivot = 0.f;
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
             float hv;
             const uint32_t src = sbuf + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + (lane & 3) * 4;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hv) : "r"(src));
+            if (rr == 0) pivot = hv;
             if (grow + rr < M) {
-              ssum += hv;
-              ssq = fmaf(hv, hv, ssq);
+              const float d = hv - pivot;
+              ssum += d;
+              ssq = fmaf(d, d, ssq);
             }
           }
-          reinterpret_cast<float2*>(stats_part)[(grow >> 5) * (static_cast<int64_t>(n_tiles) * BN) + n0 + c0 + lane] = make_float2(ssum, ssq);
+          const float cnt = static_cast<float>(M - grow < 32 ? M - grow : 32);
+          const float dm = ssum / cnt;
+          reinterpret_cast<float2*>(stats_part)[(grow >> 5) * (static_cast<int64_t>(n_tiles) * BN) + n0 + c0 + lane] =
+              make_float2(pivot + dm, fmaxf(ssq - ssum * dm, 0.f));
         }
       } else {
   #pragma unroll 1

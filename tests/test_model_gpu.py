@@ -261,6 +261,33 @@ def test_spektral_style_inputs_and_layers(small_case):
         g.GeneralConv(channels=16, aggregate="prod")
 
 
+def test_batchnorm_statistics_with_a_large_mean_to_std_ratio(small_case):
+    """Pre-BatchNorm outputs whose column means are ~40 standard deviations away from 0 (a large bias in front of the
+    BatchNorm; sum aggregation produces the same situation by itself).  Keras' variance is two-pass; the statistics the
+    tensor-core GEMM leaves in its epilogue are taken relative to a pivot row per 32-row group and combined in fp64, so
+    the variance - and with it the moving statistics, the loss and every gradient - still agrees with the float64
+    oracle to 1e-5 (E[h^2] - mean^2 in float32 would be off by ~1e-3 here)."""
+    c = small_case
+    cfg = GNNConfig(in_features=12, output=2, activation="softmax", hidden=128, message_passing=2)
+    specs = block_specs(cfg)
+    w, s = g.init_params(cfg, seed=6, perturb=True)
+    for b in specs[:-1]:
+        o, n = b.bias
+        w[o:o + n] += 40.0 * np.sign(np.random.default_rng(o).standard_normal(n)).astype(np.float32)
+    args = (cfg, specs, w, s, c["x"], c["idx"][:, 0], c["idx"][:, 1], c["seg"], c["y"], 8)
+    (x, a, i), y = next(g.DisjointLoader(c["ds"], batch_size=8, epochs=1, shuffle=False))
+    model = make_model(cfg, w, s)
+    loss_acc, probs = model.train_step_grads([x, a, i], y)
+    ref = O1.loss_and_grads(*args, prelu_branch=gpu_prelu_branches(model, cfg, c["x"].shape[0], 8))
+    ratios = [np.abs(cc["mean"]) / np.sqrt(cc["var"]) for cc in ref["ctx"]["caches"][1:4]]
+    assert min(r.min() for r in ratios) > 10.0                       # the situation the test is about
+    assert abs(host(loss_acc)[0] - ref["loss"]) < TOL * abs(ref["loss"])
+    assert rel_err(host(probs), ref["probs"]) < TOL
+    assert rel_err(host(model.state), ref["new_state"]) < TOL
+    o2 = O2.loss_and_grads(*args)
+    assert_grads_close(host(model.grads), ref["grads"], cfg, o2["grads"])
+
+
 def test_node_level_output_without_pooling(small_case):
     c = small_case
     cfg = GNNConfig(in_features=12, output=3, activation=None, hidden=16, message_passing=2, pool=None)
