@@ -24,6 +24,8 @@
 // warps (slow, correct).
 #include <cuda.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 #ifndef GCS_SLAB_ASM
@@ -280,7 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
     const __grid_constant__ Maps maps, const int32_t* __restrict__ graph_ptr, int n_graphs,
     const int32_t* __restrict__ blk_ptr, const uint32_t* __restrict__ ent, const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ alpha, const float* __restrict__ R, int64_t ldr, float* __restrict__ Y, int64_t ldy, int H,
-    int stage_bytes, int n_stages, float* __restrict__ amax, unsigned long long* __restrict__ dbg) {
+    int stage_bytes, int n_stages, float* __restrict__ amax, unsigned int* __restrict__ ticket,
+    unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // dbg (gcs_debug_slab_timing): per role {cycles waiting on its barrier, cycles working}, summed over warps and CTAs
 #ifdef GCS_SLAB_TIMING                               // development build only (scripts/slab_timing.py): costs registers
@@ -316,8 +319,13 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
     // ------------------------------------------------------------------ producer
     // The scalars of an item hang off two dependent global loads (graph_ptr -> blk_ptr); they are requested one and
     // two items ahead so that posting an item never waits for them.
-    const int64_t stride = gridDim.x;
-    // Items are walked from the LAST graph to the first: the producer of X (the dense transform in front of the
+    // Work items are handed out through a ticket counter in global memory (ticket[0]; ticket[1] counts the CTAs that
+    // have left the queue, the last one re-arms both for the next launch).  Graphs differ in length (log-normal protein
+    // lengths: the row count of an item varies by ~26 %), so with a fixed round-robin share the slowest of the 148
+    // CTAs carried ~9 % more rows than the average and every other SM idled at the end of the launch.  Which CTA
+    // runs an item changes nothing in the result.  A ticket is drawn three items ahead of its use and read one item
+    // after it was drawn, so the atomic's round trip is never waited for.
+    // Tickets run from the LAST graph to the first: the producer of X (the dense transform in front of the
     // aggregation) wrote its rows in ascending order, so the tail of X is what the 126 MB L2 still holds.
     auto graph_of = [&](int64_t w, int& off, int& n) {
       off = 0; n = 0;
@@ -336,12 +344,16 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
       }
     };
     int off, n, E0, E1, off1, n1, E0n, E1n, off2, n2;
-    graph_of(blockIdx.x, off, n);
+    unsigned int tk = 0;                             // lane 0: the ticket in flight
+    if (lane == 0) tk = atomicAdd(ticket, 3u);       // the first three items of a CTA are neighbours
+    int64_t w = static_cast<int64_t>(__shfl_sync(0xffffffffu, tk, 0)), w1 = w + 1, w2 = w + 2;
+    if (lane == 0) tk = atomicAdd(ticket, 1u);
+    graph_of(w, off, n);
     entries_of(off, n, E0, E1);
-    graph_of(blockIdx.x + stride, off1, n1);
+    graph_of(w1, off1, n1);
     int it = 0;
-    for (int64_t w = blockIdx.x; w < n_items; w += stride) {
-      graph_of(w + 2 * stride, off2, n2);            // consumed two iterations from now
+    for (; w < n_items;) {
+      graph_of(w2, off2, n2);                        // consumed two iterations from now
       entries_of(off1, n1, E0n, E1n);                // consumed next iteration
       if (n > 0) {
         const int64_t wr = n_items - 1 - w;
@@ -399,7 +411,11 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
         }
       }
       off = off1; n = n1; E0 = E0n; E1 = E1n; off1 = off2; n1 = n2;
+      w = w1; w1 = w2;
+      w2 = static_cast<int64_t>(__shfl_sync(0xffffffffu, tk, 0));   // drawn one item ago: long since returned
+      if (lane == 0) tk = atomicAdd(ticket, 1u);
     }
+    w2 = static_cast<int64_t>(__shfl_sync(0xffffffffu, tk, 0));     // the last draw has returned before the CTA leaves the queue
     GCS_TREPORT(0, 1);
     if (dbg && lane == 0) atomicAdd(dbg + 6, 1ull * it);
     const int s = it % S;                             // stop marker
@@ -407,6 +423,13 @@ __global__ void __launch_bounds__(kThreads, 1) spmm_slab_kernel(
     if (lane == 0) {
       hd->meta[s].mode = -1;
       mbar_arrive(smem_u32(&hd->landed[s]));
+      // the last CTA to leave re-arms the counters for the next launch that is given this slot
+      __threadfence();
+      if (w2 >= 0 && atomicAdd(ticket + 1, 1u) == gridDim.x - 1) {
+        ticket[0] = 0u;
+        ticket[1] = 0u;
+        __threadfence();
+      }
     }
   } else {
     // ------------------------------------------------------------------ consumers
@@ -514,6 +537,12 @@ unsigned long long* g_dbg = nullptr;   // gcs_debug_slab_timing: 8 device counte
 
 constexpr int kSmemMax = 232448;   // opt-in maximum per CTA on sm_100
 
+// Work-queue counters of the persistent kernel: {next ticket, CTAs that left} per slot, zero at module load and re-armed
+// by the last CTA of every launch.  Launches take the slots round-robin, so two launches only share a slot when more
+// than kTicketSlots aggregation kernels of one device are in flight at once (each occupies every SM).
+constexpr int kTicketSlots = 64;
+__device__ unsigned int g_tickets[2 * kTicketSlots];
+
 int stage_bytes() {
   const int most = ((kSmemMax - kHeaderBytes - 128) / g_stages) & ~127;
   return g_stage_bytes > 0 && g_stage_bytes < most ? (g_stage_bytes & ~127) : most;
@@ -613,6 +642,10 @@ int launch_slab(int64_t n_rows, const int32_t* graph_ptr, int n_graphs, const in
   GCS_CUDA(cudaGetDevice(&dev));
   int grid = slab::g_grid > 0 ? slab::g_grid : sm_count();
   if (grid > items) grid = static_cast<int>(items);
+  static unsigned int* tickets_dev[64] = {};           // per device
+  if (!tickets_dev[dev & 63]) GCS_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets_dev[dev & 63]), slab::g_tickets));
+  static std::atomic<unsigned int> launch_seq{0};
+  unsigned int* const ticket = tickets_dev[dev & 63] + 2 * (launch_seq.fetch_add(1u) % slab::kTicketSlots);
 #define GCS_SLAB_LAUNCH(T)                                                                                             \
   do {                                                                                                                 \
     static int attr_smem[64] = {};   /* per instantiation and device; the attribute only ever grows */               \
@@ -622,7 +655,7 @@ int launch_slab(int64_t n_rows, const int32_t* graph_ptr, int n_graphs, const in
     }                                                                                                                  \
     slab::spmm_slab_kernel<RB, T><<<grid, slab::kThreads, smem, st>>>(maps, graph_ptr, n_graphs, blk_ptr, ent, X, ldx, scale, \
                                                                       shift, alpha, R, ldr, Y, ldy, H, sb, slab::g_stages, \
-                                                                      amax_sink().produce, slab::g_dbg);               \
+                                                                      amax_sink().produce, ticket, slab::g_dbg);       \
   } while (0)
   if (scale) GCS_SLAB_LAUNCH(true); else GCS_SLAB_LAUNCH(false);
 #undef GCS_SLAB_LAUNCH
