@@ -36,48 +36,65 @@ namespace gcs {
 constexpr int kRB = 4;
 
 // RB-way merge of the sorted neighbour lists of one row block; kFill = false counts the union size.
+// Order of a block's entries: first the entries that ALL RB rows share (mask = all ones), in ascending column order and
+// as many as fill whole groups of four - each of these words carries kRbFullFlag, and a kernel may add such a neighbour
+// row once into an accumulator the block shares instead of RB times (in a band of half-width w, 2w - 2 of the 2w + 4
+// union columns of a 4-row block are shared by all four rows) - then every other entry in ascending column order.
+// Per output row the summation order is therefore: the row's other neighbours ascending, then the shared sum (slab
+// kernel), or shared neighbours ascending, then the others (kernels that ignore the flag) - fixed either way.
+constexpr uint32_t kRbFullFlag = 1u << 4;
 template <int RB, bool kFill>
 __global__ void __launch_bounds__(128) rb_build_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                                         int n_rows, int n_blocks, const int32_t* __restrict__ blk_ptr,
                                                         int32_t* __restrict__ count, uint32_t* __restrict__ ent) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
-  int p[RB], e[RB], cur[RB];
-#pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    const int row = b * RB + r;
-    p[r] = row < n_rows ? __ldg(rowptr + row) : 0;
-    e[r] = row < n_rows ? __ldg(rowptr + row + 1) : 0;
-    cur[r] = p[r] < e[r] ? __ldg(colidx + p[r]) : INT32_MAX;
-  }
-  int n = 0, last = 0;
-  uint32_t* out = kFill ? ent + __ldg(blk_ptr + b) : nullptr;
-  while (true) {
-    int cmin = cur[0];
-#pragma unroll
-    for (int r = 1; r < RB; ++r) cmin = min(cmin, cur[r]);
-    if (cmin == INT32_MAX) break;
-    uint32_t mask = 0;
+  constexpr uint32_t kAll = (1u << RB) - 1u;
+  // visit(col, mask) for every union entry in ascending column order
+  auto merge = [&](auto&& visit) {
+    int p[RB], e[RB], cur[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      if (cur[r] == cmin) {
-        mask |= 1u << r;
-        ++p[r];
-        cur[r] = p[r] < e[r] ? __ldg(colidx + p[r]) : INT32_MAX;
-      }
+      const int row = b * RB + r;
+      p[r] = row < n_rows ? __ldg(rowptr + row) : 0;
+      e[r] = row < n_rows ? __ldg(rowptr + row + 1) : 0;
+      cur[r] = p[r] < e[r] ? __ldg(colidx + p[r]) : INT32_MAX;
     }
-    if (kFill) out[n] = (static_cast<uint32_t>(cmin) << 8) | mask;
-    ++n;
-    last = cmin;
-  }
+    while (true) {
+      int cmin = cur[0];
+#pragma unroll
+      for (int r = 1; r < RB; ++r) cmin = min(cmin, cur[r]);
+      if (cmin == INT32_MAX) break;
+      uint32_t mask = 0;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (cur[r] == cmin) {
+          mask |= 1u << r;
+          ++p[r];
+          cur[r] = p[r] < e[r] ? __ldg(colidx + p[r]) : INT32_MAX;
+        }
+      }
+      visit(cmin, mask);
+    }
+  };
+  int n = 0, n_full = 0, last = 0;
+  merge([&](int col, uint32_t mask) { ++n; n_full += mask == kAll ? 1 : 0; last = col; });
   // pad to a multiple of 4 entries with no-ops (mask 0, a column of the block): every block then starts on a 16-byte
   // boundary and the kernels read four entry words per load
   const int padded = (n + 3) & ~3;
-  if (kFill) {
-    for (; n < padded; ++n) out[n] = static_cast<uint32_t>(last) << 8;
-  } else {
+  if (!kFill) {
     count[b] = padded;
+    return;
   }
+  uint32_t* out = ent + __ldg(blk_ptr + b);
+  const int lead = n_full & ~3;                      // shared entries that form whole groups of four
+  int i_full = 0, i_rest = lead;
+  merge([&](int col, uint32_t mask) {
+    const uint32_t w = (static_cast<uint32_t>(col) << 8) | mask;
+    if (mask == kAll && i_full < lead) out[i_full++] = w | kRbFullFlag;
+    else out[i_rest++] = w;
+  });
+  for (; i_rest < padded; ++i_rest) out[i_rest] = static_cast<uint32_t>(last) << 8;
 }
 
 // One row block per `lanes` threads (lanes = H/4, each lane owns 4 columns); a CTA walks a contiguous
@@ -115,8 +132,6 @@ __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
     if (b >= n_blocks) break;
     const int e0 = __ldg(blk_ptr + b), e1 = __ldg(blk_ptr + b + 1);
     float4 acc[kRB];
-#pragma unroll
-    for (int r = 0; r < kRB; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     // Predicated adds: 4 * kRB issue slots per entry of which about a third do work.  Measured alternatives on B200
     // (8-row blocks): warp-uniform branches per row / per half block 427 us, packed add.f32x2 434 us, predicated 367 us.
     auto scatter = [&](const float4& v, uint32_t m) {
@@ -126,6 +141,23 @@ __global__ void __launch_bounds__(256, 4) spmm_rb4_kernel(
       }
     };
     int e = e0;
+    {
+      // leading groups of neighbours that all rows of the block have (kRbFullFlag): one shared sum, 4 adds per
+      // neighbour instead of 16 predicated ones; the rows start from it (the order of the list, bit for bit)
+      float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (; e + 4 <= e1; e += 4) {
+        const uint32_t w0 = __ldg(ent + e);
+        if (!(w0 & kRbFullFlag)) break;
+        const uint32_t w1 = __ldg(ent + e + 1), w2 = __ldg(ent + e + 2), w3 = __ldg(ent + e + 3);
+        const float4 v0 = load(w0), v1 = load(w1), v2 = load(w2), v3 = load(w3);
+        sh.x += v0.x; sh.y += v0.y; sh.z += v0.z; sh.w += v0.w;
+        sh.x += v1.x; sh.y += v1.y; sh.z += v1.z; sh.w += v1.w;
+        sh.x += v2.x; sh.y += v2.y; sh.z += v2.z; sh.w += v2.w;
+        sh.x += v3.x; sh.y += v3.y; sh.z += v3.z; sh.w += v3.w;
+      }
+#pragma unroll
+      for (int r = 0; r < kRB; ++r) acc[r] = sh;
+    }
     for (; e + 4 <= e1; e += 4) {
       const uint32_t w0 = __ldg(ent + e), w1 = __ldg(ent + e + 1), w2 = __ldg(ent + e + 2), w3 = __ldg(ent + e + 3);
       const float4 v0 = load(w0), v1 = load(w1), v2 = load(w2), v3 = load(w3);

@@ -218,8 +218,15 @@ __device__ __forceinline__ float gather_slab(const Meta& m, uint32_t slab, uint3
       e1 -= m.e0;
       uint32_t ea = sent + 4u * e0;
       const uint32_t eb = sent + 4u * e1;
+      // (The RB list leads with groups of neighbours that all rows of the block share, flagged for a shared accumulator:
+      // spmm_rb4_kernel uses it - it is bound by issue slots.  Here it was measured and brings nothing, 386 / 354 us
+      // against 380 / 349 us at degree 32 with 40 % fewer adds: this kernel's time follows its shared-memory wavefronts,
+      // 46 M at degree 12, 67 M at degree 32.  The summation order is that of the list either way, so both kernels agree
+      // bit for bit.)
       for (; ea < eb; ea += 16) {
         const uint4 w = lds128u(ea);
+        // (no-op words - padding, the neighbouring graph's entries of a straddling block - still gather slab row 0:
+        // predicating those loads off saves ~6 % of the gather wavefronts and was measured 10 % SLOWER, 290 / 261 us)
         const float4 v0 = lds128((w.x & kAddrMask) | qoff), v1 = lds128((w.y & kAddrMask) | qoff);
         const float4 v2 = lds128((w.z & kAddrMask) | qoff), v3 = lds128((w.w & kAddrMask) | qoff);
         scatter<RB>(acc, v0, w.x); scatter<RB>(acc, v1, w.y); scatter<RB>(acc, v2, w.z); scatter<RB>(acc, v3, w.w);

@@ -57,7 +57,7 @@ def run(a, H, mode, iters, transform=True, flush=None, check=None, ldy=None):
         lib.gcs_debug_set_spmm_mode(1)
         ref = ops.spmm_sum(a.rowptr, a.colidx, x, *args)
         lib.gcs_debug_set_spmm_mode({"rows": 1, "rb4": 2}.get(mode, 0))
-        ok = bool(torch.equal(ref, y))
+        ok = float((ref - y).abs().max() / ref.abs().max())   # a reordered float32 sum: ~1e-7
     times = []
     for _ in range(iters):
         if flush is not None:
@@ -75,7 +75,7 @@ def run(a, H, mode, iters, transform=True, flush=None, check=None, ldy=None):
            "union_ratio": ratio, "alg_GBs": round(alg / t / 1e9, 1), "frac_measured_hbm": round(alg / t / 1e9 / peak(), 4),
            "edges_per_s": a.nnz / t}
     if ok is not None:
-        out["bitwise_equal_rows_kernel"] = ok
+        out["max_rel_diff_vs_rows_kernel"] = ok
     return out
 
 
