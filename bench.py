@@ -24,6 +24,7 @@ graph across ranks (weak scaling: 1024 graphs per GPU per step).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -71,7 +72,7 @@ def _ncu_traffic():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,clocks.mem,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -94,9 +95,11 @@ class ClockSampler:
             time.sleep(0.01)
 
     def start(self):
+        if os.environ.get("GCS_BENCH_NO_SAMPLER"):        # diagnostic: is a stall in the timed region the sampler's doing?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("GCS_BENCH_SAMPLE_MS", "20")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -397,15 +400,43 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(loop_body, n_steps):
-        """CUDA-event time of n_steps, max over ranks (ms)."""
+    per_step = {}
+
+    def timed(loop_body, n_steps, tag=None):
+        """CUDA-event time of n_steps, max over ranks (ms).  With a tag, an event after every step as well (the per-step
+        times go into the JSON line as a diagnostic: a stall of the queue - an allocation, a host hiccup - shows as one
+        long step)."""
+        # CPython's cyclic collector stays out of the timed region: a full collection walks every tracked object of the
+        # process (torch + numpy + scipy: ~10^6) and pauses the launching thread for 50-200 ms, which showed up as one
+        # 100-190 ms step in about one of five 10-step regions (measured with and without the clock sampler); a
+        # training loop that cares does the same (gc.freeze() after set-up, collections between epochs)
+        use_gc = not os.environ.get("GCS_BENCH_KEEP_GC")
+        if use_gc:
+            gc.collect()
+            gc.disable()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)] if tag else []
+        host = []
         e0.record()
-        for _ in range(n_steps):
+        for k in range(n_steps):
+            th = time.perf_counter()
             loop_body()
+            if tag:
+                marks[k].record()
+                host.append(round((time.perf_counter() - th) * 1e3, 3))
         e1.record()
         barrier()
+        if use_gc:
+            gc.enable()
+        if tag:
+            per_step[tag + "_host_enqueue"] = host
+        if tag:
+            prev, out = e0, []
+            for m in marks:
+                out.append(round(prev.elapsed_time(m), 3))
+                prev = m
+            per_step[tag] = out
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -427,9 +458,11 @@ def run_b200(args):
     for _ in range(W):
         step()
     launches0 = lib.gcs_debug_launch_count()
+    segs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
     sampler.mark_begin()
-    ms_total = timed(step, K)
+    ms_total = timed(step, K, "value")
     sampler.mark_end()
+    per_step["device_allocs_in_timed_region"] = torch.cuda.memory_stats().get("num_device_alloc", 0) - segs0
     launches = lib.gcs_debug_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / K
@@ -522,7 +555,7 @@ def run_b200(args):
         io["k"] = k + 1
     for _ in range(W):
         step_e2e()
-    ms_e2e = timed(step_e2e, K)
+    ms_e2e = timed(step_e2e, K, "e2e")
     e2e_value = world * B * K / (ms_e2e / 1e3)
 
     if rank != 0:
@@ -569,6 +602,7 @@ def run_b200(args):
         "fwd_with_batching_ms_per_step": ms_fwd_batched,
         "edges_per_sec_train_step": world * nnz / (ms_step / 1e3),
         "ops": ops_report,
+        "per_step_ms": per_step,
     }
     emit(line)
     if world > 1:

@@ -13,6 +13,7 @@
 // every shared-memory read is a conflict-free 128-bit load), register-prefetched double
 // buffering: one __syncthreads per 16-deep slice.
 #include "common.cuh"
+#include "prep.cuh"
 
 namespace gcs {
 
@@ -368,6 +369,20 @@ bool wgrad_f16_ok(int K);
 }  // namespace tc
 }  // namespace gcs
 
+namespace gcs {
+PreparedTable*& prepared_table() {
+  thread_local PreparedTable* t = nullptr;
+  return t;
+}
+void* find_prepared(int kind, const float* w, int kred, int nout) {
+  const PreparedTable* t = prepared_table();
+  if (!t) return nullptr;
+  for (int i = 0; i < t->n; ++i)
+    if (t->e[i].kind == kind && t->e[i].w == w && t->e[i].kred == kred && t->e[i].nout == nout) return t->e[i].ws;
+  return nullptr;
+}
+}  // namespace gcs
+
 using namespace gcs;
 
 static int g_gemm_mode = 0;   // 0 = auto (tensor cores when the shape allows), 1 = CUDA cores only, 2 = tensor cores or error
@@ -389,16 +404,20 @@ static int try_tensor_cores(const float* A, int64_t lda, const float* W, int w_r
   // (amax_sink().consume), or - debug mode 2 - from an extra pass over A.
   const float* a_amax = amax_sink().consume;
   if (tc::f16_mode() && tc::f16_shape_ok(Kred) && (a_amax || tc::f16_mode() == 2)) {
-    char* hi = static_cast<char*>(workspace);
+    void* const ready = (a_amax && !transpose_w) ? find_prepared(2, W, Kred, Nout) : nullptr;   // split at the start of the step
+    void* const wsp = ready ? ready : workspace;
+    char* hi = static_cast<char*>(wsp);
     char* lo = hi + 2LL * Kred * Nout;
-    float* cells = tc::f16_cells(workspace, Kred, Nout);
-    GCS_TRY(tc::f16_begin(cells, st));
-    GCS_TRY(tc::absmax(W, w_cols, w_rows, w_cols, cells, st));
-    if (!a_amax) {
-      GCS_TRY(tc::absmax(A, lda, M, Kred, cells + 2, st));
-      a_amax = cells + 2;
+    float* cells = tc::f16_cells(wsp, Kred, Nout);
+    if (!ready) {
+      GCS_TRY(tc::f16_begin(cells, st));
+      GCS_TRY(tc::absmax(W, w_cols, w_rows, w_cols, cells, st));
+      if (!a_amax) {
+        GCS_TRY(tc::absmax(A, lda, M, Kred, cells + 2, st));
+        a_amax = cells + 2;
+      }
+      GCS_TRY(tc::split_f16_strided(W, w_rows, w_cols, w_cols, transpose_w, transpose_w ? w_rows : w_cols, hi, lo, cells, st));
     }
-    GCS_TRY(tc::split_f16_strided(W, w_rows, w_cols, w_cols, transpose_w, transpose_w ? w_rows : w_cols, hi, lo, cells, st));
     GCS_TRY(tc::launch_f16(A, lda, hi, lo, cells, a_amax, bias, C, ldc, M, Kred, Nout, accumulate, st));
     *used = 1;
     return GCS_OK;
@@ -447,18 +466,22 @@ int linear_fwd_fused(const float* A, int64_t lda, const float* W, const float* b
       !tc::shape_ok(M, K, N, A, lda, C, ldc, bias) || !workspace || !aligned16(workspace) || workspace_bytes < need ||
       (alpha && !aligned16(alpha)))
     return GCS_OK;
-  char* hi = static_cast<char*>(workspace);
+  void* const ready = scale ? nullptr : find_prepared(0, W, K, N);      // split at the start of the step (training)
+  void* const wsp = ready ? ready : workspace;
+  char* hi = static_cast<char*>(wsp);
   char* lo = hi + 2LL * K * N;
-  float* cells = tc::f16_cells(workspace, K, N);
+  float* cells = tc::f16_cells(wsp, K, N);
   const float* b = bias;
-  GCS_TRY(tc::f16_begin(cells, st));
-  GCS_TRY(tc::absmax(W, N, K, N, cells, st, scale));
-  if (scale) {
-    float* bias2 = cells + 64;
-    GCS_TRY(tc::fold_bias(bias, scale, shift, N, bias2, st));
-    b = bias2;
+  if (!ready) {
+    GCS_TRY(tc::f16_begin(cells, st));
+    GCS_TRY(tc::absmax(W, N, K, N, cells, st, scale));
+    if (scale) {
+      float* bias2 = cells + 64;
+      GCS_TRY(tc::fold_bias(bias, scale, shift, N, bias2, st));
+      b = bias2;
+    }
+    GCS_TRY(tc::split_f16_strided(W, K, N, N, true, K, hi, lo, cells, st, scale));
   }
-  GCS_TRY(tc::split_f16_strided(W, K, N, N, true, K, hi, lo, cells, st, scale));
   if (amax_out) GCS_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
   GCS_TRY(tc::launch_f16(A, lda, hi, lo, cells, a_amax, b, C, ldc, M, K, N, 0, st, nullptr, 0, nullptr, alpha, amax_out, stats_part));
   *used = 1;
@@ -480,19 +503,23 @@ int dense_dx_concat(const float* dh, int64_t ld, const float* const* W, const in
                      (!rowbias || (ld_rowbias % 4 == 0 && aligned16(rowbias)));
   const float* a_amax = amax_sink().consume;
   if (tc_ok && tc::f16_mode() && tc::f16_shape_ok(Kred) && (a_amax || tc::f16_mode() == 2)) {
-    char* hi = static_cast<char*>(workspace);
+    void* const ready = a_amax ? find_prepared(1, W[0] + static_cast<int64_t>(row_off[0]) * Hred, Kred, Nout) : nullptr;
+    void* const wsp = ready ? ready : workspace;
+    char* hi = static_cast<char*>(wsp);
     char* lo = hi + 2LL * Kred * Nout;
-    float* cells = tc::f16_cells(workspace, Kred, Nout);
-    GCS_TRY(tc::f16_begin(cells, st));
-    for (int b = 0; b < n_blocks; ++b)
-      GCS_TRY(tc::absmax(W[b] + static_cast<int64_t>(row_off[b]) * Hred, Hred, Nout, Hred, cells, st));
-    if (!a_amax) {
-      GCS_TRY(tc::absmax(dh, ld, M, Kred, cells + 2, st));
-      a_amax = cells + 2;
+    float* cells = tc::f16_cells(wsp, Kred, Nout);
+    if (!ready) {
+      GCS_TRY(tc::f16_begin(cells, st));
+      for (int b = 0; b < n_blocks; ++b)
+        GCS_TRY(tc::absmax(W[b] + static_cast<int64_t>(row_off[b]) * Hred, Hred, Nout, Hred, cells, st));
+      if (!a_amax) {
+        GCS_TRY(tc::absmax(dh, ld, M, Kred, cells + 2, st));
+        a_amax = cells + 2;
+      }
+      for (int b = 0; b < n_blocks; ++b)   // Bt[c][b*Hred + n] = W_b[row_off_b + c][n]
+        GCS_TRY(tc::split_f16_strided(W[b] + static_cast<int64_t>(row_off[b]) * Hred, Nout, Hred, Hred, false, Kred,
+                                      hi + 2LL * b * Hred, lo + 2LL * b * Hred, cells, st));
     }
-    for (int b = 0; b < n_blocks; ++b)   // Bt[c][b*Hred + n] = W_b[row_off_b + c][n]
-      GCS_TRY(tc::split_f16_strided(W[b] + static_cast<int64_t>(row_off[b]) * Hred, Nout, Hred, Hred, false, Kred,
-                                    hi + 2LL * b * Hred, lo + 2LL * b * Hred, cells, st));
     return tc::launch_f16(dh, ld, hi, lo, cells, a_amax, nullptr, C, ldc, M, Kred, Nout, accumulate, st, rowbias, ld_rowbias, seg);
   }
   if (tc_ok) {

@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "prep.cuh"
 
 namespace gcs {
 namespace tc {
@@ -609,8 +610,8 @@ __global__ void __launch_bounds__(256) split_weights_kernel(const float* __restr
 }
 
 // |max| of a strided matrix into *cell (pre-zeroed; non-negative floats order like their bit patterns).
-__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int K, float* cell,
-                                                     const float* __restrict__ col_scale) {
+__device__ __forceinline__ void absmax_body(const float* __restrict__ A, int64_t lda, int64_t M, int K, float* cell,
+                                            const float* __restrict__ col_scale) {
   float m = 0.f;
   for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
     const float* row = A + r * lda;
@@ -618,6 +619,10 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A
       m = fmaxf(m, fabsf(col_scale ? __ldg(row + c) * __ldg(col_scale + c) : __ldg(row + c)));
   }
   amax_commit(m, cell);
+}
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int K, float* cell,
+                                                     const float* __restrict__ col_scale) {
+  absmax_body(A, lda, M, K, cell, col_scale);
 }
 
 // Inference fold of BatchNorm into the bias of the dense layer in front of it: b' = b * scale + shift.
@@ -634,11 +639,10 @@ __global__ void amax_merge_kernel(float* cell, const float* other) {
 
 // fp16 split of the weights for linear_tc_pair_kernel<true>: hi = fp16(w * s), lo = fp16((w * s - hi) * 2^11) with
 // s = f16_scale(*amax); *scale_inv = 1 / s for the epilogue.
-__global__ void __launch_bounds__(256) split_weights_f16_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
-                                                                int transpose, int64_t ldo, __half* __restrict__ hi,
-                                                                __half* __restrict__ lo, const float* __restrict__ amax,
-                                                                float* __restrict__ scale_inv,
-                                                                const float* __restrict__ col_scale) {
+__device__ __forceinline__ void split_weights_f16_body(const float* __restrict__ W, int rows, int cols, int64_t ldw,
+                                                       int transpose, int64_t ldo, __half* __restrict__ hi,
+                                                       __half* __restrict__ lo, const float* __restrict__ amax,
+                                                       float* __restrict__ scale_inv, const float* __restrict__ col_scale) {
   const float s = f16_scale(__ldg(amax));
   if (blockIdx.x == 0 && threadIdx.x == 0) *scale_inv = 1.f / s;
   const int64_t n = static_cast<int64_t>(rows) * cols;
@@ -652,6 +656,27 @@ __global__ void __launch_bounds__(256) split_weights_f16_kernel(const float* __r
     hi[o] = h;
     lo[o] = __float2half_rn((y - __half2float(h)) * 2048.f);
   }
+}
+__global__ void __launch_bounds__(256) split_weights_f16_kernel(const float* __restrict__ W, int rows, int cols, int64_t ldw,
+                                                                int transpose, int64_t ldo, __half* __restrict__ hi,
+                                                                __half* __restrict__ lo, const float* __restrict__ amax,
+                                                                float* __restrict__ scale_inv,
+                                                                const float* __restrict__ col_scale) {
+  split_weights_f16_body(W, rows, cols, ldw, transpose, ldo, hi, lo, amax, scale_inv, col_scale);
+}
+
+// All weight blocks of a train step in two launches (blockIdx.y = job): the |max| cells first (several blocks may share
+// one cell: the blocks of a concatenated operand), then the splits.  The per-GEMM form above costs a memset, a |max|
+// kernel and a split kernel per weight block - ~45 launches of a few microseconds each per step at the default
+// architecture, every one of them a bubble between two large kernels.
+__global__ void __launch_bounds__(256) absmax_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+  const SplitJob& j = jobs.j[blockIdx.y];
+  absmax_body(j.W, j.ldw, j.rows, j.cols, j.cells, nullptr);
+}
+__global__ void __launch_bounds__(256) split_weights_f16_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+  const SplitJob& j = jobs.j[blockIdx.y];
+  split_weights_f16_body(j.W, j.rows, j.cols, j.ldw, j.transpose, j.ldo, static_cast<__half*>(j.hi), static_cast<__half*>(j.lo),
+                         j.cells, j.cells + 1, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1308,6 +1333,19 @@ int split_f16_strided(const float* W, int rows, int cols, int64_t ldw, bool tran
                                                                         static_cast<__half*>(hi), static_cast<__half*>(lo),
                                                                         cells, cells + 1, col_scale);
   GCS_CHECK_LAUNCH("split_weights_f16_kernel");
+  return GCS_OK;
+}
+
+// Batched form of absmax + split_f16_strided over n jobs; every job's cells must have been zeroed (the caller clears the
+// whole region the jobs live in with one memset).
+int split_f16_multi(const SplitJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return GCS_OK;
+  if (jobs.n > kMaxSplitJobs) return fail(GCS_ERR_INVALID_ARGUMENT, "split_f16_multi: too many jobs");
+  const dim3 grid(96, static_cast<unsigned>(jobs.n));
+  absmax_multi_kernel<<<grid, 256, 0, st>>>(jobs);
+  GCS_CHECK_LAUNCH("absmax_multi_kernel");
+  split_weights_f16_multi_kernel<<<grid, 256, 0, st>>>(jobs);
+  GCS_CHECK_LAUNCH("split_weights_f16_multi_kernel");
   return GCS_OK;
 }
 

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "prep.cuh"
 
 namespace gcs {
 
@@ -147,6 +148,8 @@ struct Plan {
   float* dpooled = nullptr;     // [B, Wc]
   void* lw_ws = nullptr;
   int64_t lw_ws_bytes = 0;
+  void* prep_ws = nullptr;      // fp16-split weights of every tensor-core GEMM of the step (prepare_step_weights)
+  int64_t prep_ws_bytes = 0;
   float* amax = nullptr;        // [0] running |max| of the node-level activations, [1] of the pre-BatchNorm gradients dh
   float* stat_part = nullptr;   // [ceil(N/32)][H][2] {sum, sum of squares} per 32-row group, left by the GEMM epilogue
 };
@@ -161,6 +164,83 @@ struct AmaxScope {
   }
   ~AmaxScope() { amax_sink() = saved; }
 };
+
+// The tensor-core GEMMs of one training step whose weight operand can be split ahead of time, in the shapes and under
+// the keys run_forward / run_backward will ask for (linear.cu: find_prepared): the dense transform of every node-level
+// block but the first (kind 0), the concatenated input-gradient GEMMs of the 'cat' layout (kind 1), the plain
+// input-gradient GEMMs of the pre-MLP and of the 'sum' / None layouts (kind 2).  Returns the bytes they need; with
+// base != NULL fills the split jobs and the lookup table.  A GEMM that is not listed (or whose wrapper decides against
+// the fp16 path) prepares its own operand as before.
+static int64_t list_step_weights(const gcs_model_config& c, const Plan& p, const float* params, char* base,
+                                 tc::SplitJobs* jobs, PreparedTable* table) {
+  const int H = p.H, L = p.L, P = p.P;
+  int64_t used = 0;
+  int n_jobs = 0, n_ent = 0;
+  auto region = [&](int kred, int nout) { const int64_t at = used; used += round_up(tc::f16_workspace_bytes(kred, nout), 256); return at; };
+  auto add_entry = [&](int kind, const float* w, int kred, int nout, int64_t at) {
+    if (table) table->e[n_ent] = PreparedWeights{kind, w, kred, nout, base + at};
+    ++n_ent;
+  };
+  auto add_job = [&](const float* W, int rows, int cols, int transpose, int64_t ldo, int64_t at, int64_t half_off, int kred, int nout) {
+    if (jobs) {
+      char* ws = base + at;
+      jobs->j[n_jobs] = tc::SplitJob{W, rows, cols, cols, transpose, ldo, ws + 2 * half_off, ws + 2LL * kred * nout + 2 * half_off,
+                                     tc::f16_cells(ws, kred, nout)};
+    }
+    ++n_jobs;
+  };
+  auto room = [&](int more) { return n_jobs + more <= tc::kMaxSplitJobs && n_ent < tc::kMaxSplitJobs; };
+  if (H % 64 != 0) return 0;
+  for (int bi = 1; bi < P + L; ++bi) {                          // forward: h = in . W, W [k_in, H] -> Bt [H][k_in]
+    const BlockDesc& b = p.blocks[bi];
+    if (b.k_in % 64 != 0 || b.m_out != H || !room(1)) continue;
+    const float* W = params + b.kernel();
+    const int64_t at = region(b.k_in, H);
+    add_entry(0, W, b.k_in, H, at);
+    add_job(W, b.k_in, H, 1, b.k_in, at, 0, b.k_in, H);
+  }
+  if (c.connectivity == 1) {
+    // dLoss/d(block k of cat) = sum over the later layers' dh . W[rows of block k]^T: one long-K GEMM per block
+    for (int k = L - 2; k >= -1; --k) {                         // k = -1: the pre-MLP output block, read by all L layers
+      const int nb = L - 1 - k;
+      if (nb <= 0 || !room(nb)) continue;
+      const int kred = nb * H;
+      const int64_t at = region(kred, H);
+      for (int q = 0; q < nb; ++q) {
+        const int kp = k + 1 + q;
+        const float* W = params + p.blocks[P + kp].kernel() + static_cast<int64_t>(kp - 1 - k) * H * H;
+        if (q == 0) add_entry(1, W, kred, H, at);
+        add_job(W, H, H, 0, kred, at, static_cast<int64_t>(q) * H, kred, H);
+      }
+    }
+  }
+  for (int bi = P + L - 1; bi >= 1; --bi) {                     // plain input gradient: din = dh . W^T, W [k_in, m_out] as stored
+    const bool conv = bi >= P;
+    if (conv && c.connectivity == 1) continue;
+    const BlockDesc& b = p.blocks[bi];
+    if (b.m_out % 64 != 0 || !room(1)) continue;
+    const float* W = params + b.kernel();
+    const int64_t at = region(b.m_out, b.k_in);
+    add_entry(2, W, b.m_out, b.k_in, at);
+    add_job(W, b.k_in, b.m_out, 0, b.m_out, at, 0, b.m_out, b.k_in);
+  }
+  if (jobs) jobs->n = n_jobs;
+  if (table) table->n = n_ent;
+  return used;
+}
+
+// Splits every listed weight operand in two launches (+ one memset of the cells) at the start of a training step; the
+// table stays valid until the parameters change (the optimizer step after the backward).
+static int prepare_step_weights(const gcs_model_config& c, const Plan& p, const float* params, PreparedTable* table,
+                                gcs_stream st) {
+  table->n = 0;
+  if (!p.prep_ws || p.prep_ws_bytes <= 0 || tc::f16_mode() != 1) return GCS_OK;
+  tc::SplitJobs jobs;
+  jobs.n = 0;
+  list_step_weights(c, p, params, static_cast<char*>(p.prep_ws), &jobs, table);
+  GCS_CUDA(cudaMemsetAsync(p.prep_ws, 0, p.prep_ws_bytes, as_stream(st)));
+  return tc::split_f16_multi(jobs, as_stream(st));
+}
 
 static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training, void* ws, Plan& p, int64_t* total) {
   build_blocks(c, p.blocks);
@@ -229,6 +309,8 @@ static void make_plan(const gcs_model_config& c, int64_t N, int B, bool training
     }
     p.lw_ws_bytes = lw;
     p.lw_ws = a.take<char>(lw);
+    p.prep_ws_bytes = list_step_weights(c, p, nullptr, nullptr, nullptr, nullptr);
+    p.prep_ws = a.take<char>(p.prep_ws_bytes);
   }
   *total = a.used;
 }
@@ -641,6 +723,9 @@ extern "C" int gcs_model_train_step(const gcs_model_config* cfg, const float* pa
   if (workspace_bytes < total)
     return fail(GCS_ERR_WORKSPACE, "gcs_model_train_step: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
   GCS_CHECK_ARG(p.rows_post < INT32_MAX, "gcs_model_train_step: too many output rows");
+  PreparedTable prepared;
+  GCS_TRY(prepare_step_weights(c, p, params, &prepared, stream));
+  PreparedScope prepared_scope(&prepared);
   GCS_TRY(run_forward(c, p, params, state, bt, true, stream));
   GCS_TRY(gcs_softmax_xent(p.logits, bt.y, static_cast<int32_t>(p.rows_post), p.C, probs, loss_acc, p.dlogits,
                            grad_scale, stream));
@@ -708,6 +793,9 @@ extern "C" int gcs_model_train_step_dp(const gcs_model_config* cfg, const float*
     return fail(GCS_ERR_WORKSPACE, "gcs_model_train_step_dp: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)total);
   GCS_CHECK_ARG(p.rows_post < INT32_MAX, "gcs_model_train_step_dp: too many output rows");
   HookScope hook(comm, sync_batchnorm != 0 && gcs_comm_world_size(comm) > 1);
+  PreparedTable prepared;
+  GCS_TRY(prepare_step_weights(c, p, params, &prepared, stream));
+  PreparedScope prepared_scope(&prepared);
   GCS_TRY(run_forward(c, p, params, state, bt, true, stream));
   GCS_TRY(gcs_softmax_xent(p.logits, bt.y, static_cast<int32_t>(p.rows_post), p.C, probs, loss_acc, p.dlogits, grad_scale, stream));
   cudaEvent_t* ev = dp_events();

@@ -221,6 +221,52 @@ class SparseAdjacency:
         return self._t
 
 
+class _PinnedRing:
+    """Small host -> device uploads of the steady-state loop (graph ids of a batch, the epoch's permutation, gather
+    offsets) staged through a ring of PERSISTENT pinned buffers.  ``tensor.pin_memory()`` per step looks harmless - the
+    host allocator caches its blocks - but every miss is a ``cudaHostAlloc``, which takes the driver's lock and was
+    measured to stall the launching thread for 30-190 ms now and then (one such step at every epoch boundary of
+    bench.py in about one run out of five).  A slot is reused only after the copy out of it has run (its event)."""
+
+    def __init__(self, depth=4):
+        self.bufs, self.events, self.k = [None] * depth, [None] * depth, 0
+
+    def stage(self, arr):
+        """A pinned tensor holding a copy of the NumPy array ``arr``; pass the returned slot to ``uploaded``."""
+        torch = _lib.require_cuda()
+        arr = np.ascontiguousarray(arr)
+        k = self.k
+        self.k = (k + 1) % len(self.bufs)
+        if self.events[k] is not None:
+            self.events[k].synchronize()                       # long since complete in a running loop
+            self.events[k] = None
+        nbytes = max(int(arr.nbytes), 8)
+        if self.bufs[k] is None or self.bufs[k].numel() < nbytes:
+            # set-up / growth only, and for ALL slots at once: the first use pays every cudaHostAlloc of the ring
+            for e in self.events:
+                if e is not None:
+                    e.synchronize()
+            self.events = [None] * len(self.bufs)
+            self.bufs = [torch.empty(2 * nbytes, dtype=torch.uint8).pin_memory() for _ in self.bufs]
+        t = self.bufs[k][:arr.nbytes].view(getattr(torch, str(arr.dtype))).view(arr.shape)
+        t.numpy()[...] = arr
+        return t, k
+
+    def uploaded(self, k):
+        """Call after enqueueing the copy out of slot k on the current stream."""
+        torch = _lib.require_cuda()
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+
+    def upload(self, arr):
+        """Stage + asynchronous copy to a fresh device tensor on the current stream."""
+        t, k = self.stage(arr)
+        dev = t.cuda(non_blocking=True)
+        self.uploaded(k)
+        return dev
+
+
 class DeviceGraphStore:
     """The packed dataset resident in HBM + the host-side per-graph sizes."""
 
@@ -250,12 +296,12 @@ class DeviceGraphStore:
         i32 = dict(dtype=torch.int32, device="cuda")
         graph_ptr = torch.empty(b + 1, **i32)
         edge_ptr = torch.empty(b + 1, **i32)
-        rowptr = torch.empty(n + 1, **i32)
-        colidx = torch.empty(nnz, **i32)
-        x = torch.empty(n, self.n_feat, dtype=torch.float32, device="cuda")
-        seg = torch.empty(n, dtype=torch.int64, device="cuda")
+        rowptr = ops.empty_bucketed(n + 1, dtype=torch.int32)          # bucketed sizes: no cudaMalloc inside a running loop
+        colidx = ops.empty_bucketed(nnz, dtype=torch.int32)
+        x = ops.empty_bucketed(n, self.n_feat, dtype=torch.float32)
+        seg = ops.empty_bucketed(n, dtype=torch.int64)
         y = torch.empty(b, self.n_classes, dtype=torch.float32, device="cuda") if (want_labels and self.y is not None) else None
-        coo = torch.empty(nnz, 2, dtype=torch.int64, device="cuda") if want_coo else None
+        coo = ops.empty_bucketed(nnz, 2, dtype=torch.int64) if want_coo else None
         flag = torch.zeros(1, **i32)
         check(lib.gcs_batch_disjoint(ptr(self.node_off), ptr(self.rowptr), ptr(self.col), ptr(self.x), ptr(self.y),
                                      self.n_feat, max(self.n_classes, 1), ptr(graph_ids_dev), b, n, nnz,
@@ -300,6 +346,7 @@ class HostGraphStore:
         self.y = pin(packed.y.astype(np.float32, copy=False)) if self.n_classes else None
         self.symmetric = symmetric
         self.h2d_bytes_last = 0
+        self._ring = _PinnedRing(depth=6)
 
     def _gather(self, ids):
         """Pack the graphs ``ids`` (any order) into a fresh pinned mini-dataset."""
@@ -339,7 +386,7 @@ class HostGraphStore:
             dev = list(parts)
             # uploaded on THIS stream: with prefetch the kernel runs on a side stream, which is not ordered after the
             # loader's asynchronous upload of the epoch order (graph_ids_dev)
-            ids_dev = ids_local.pin_memory().cuda(non_blocking=True)
+            ids_dev = self._ring.upload(ids_local.numpy())
             # bytes the kernel pulls over the host link: per graph its node offsets, row pointers, columns, features, label
             self.h2d_bytes_last = 16 * b + 8 * (n + b) + 4 * nnz + 4 * self.n_feat * n + 4 * self.n_classes * b + 8 * b
         elif parts is None:
@@ -348,31 +395,38 @@ class HostGraphStore:
             np.cumsum(self.h_n_nodes[ids], out=off[0, 1:])
             np.cumsum(self.h_n_edges[ids], out=off[1, 1:])
             off[2, :b] = ids
-            off_dev = torch.from_numpy(off).pin_memory().cuda(non_blocking=True)
+            off_dev = self._ring.upload(off)
             d_node_off = off_dev[0]
-            d_rowptr = torch.empty(n + 1, dtype=torch.int64, device="cuda")
-            d_col = torch.empty(max(nnz, 1), dtype=torch.int32, device="cuda")
-            d_x = torch.empty(max(n, 1), self.n_feat, dtype=torch.float32, device="cuda")
+            d_rowptr = ops.empty_bucketed(n + 1, dtype=torch.int64)
+            d_col = ops.empty_bucketed(max(nnz, 1), dtype=torch.int32)
+            d_x = ops.empty_bucketed(max(n, 1), self.n_feat, dtype=torch.float32)
             d_y = torch.empty(b, self.n_classes, dtype=torch.float32, device="cuda") if self.y is not None else None
             check(lib.gcs_gather_graphs(ptr(off_dev[2]), b, ptr(self.node_off), ptr(self.rowptr), ptr(self.col), ptr(self.x),
                                         ptr(self.y), self.n_feat, self.n_classes, ptr(off_dev[0]), ptr(off_dev[1]),
                                         ptr(d_rowptr), ptr(d_col), ptr(d_x), ptr(d_y), stream_ptr()), "gcs_gather_graphs")
             dev = [d_node_off, d_rowptr, d_col, d_x, d_y]
-            ids_dev = ids_local.pin_memory().cuda(non_blocking=True)
+            ids_dev = self._ring.upload(ids_local.numpy())
             self.h2d_bytes_last = 16 * b + 8 * (n + b) + 4 * nnz + 4 * self.n_feat * n + 4 * self.n_classes * b + 24 * (b + 1)
         else:
-            dev = [t.cuda(non_blocking=True) if t is not None else None for t in parts]
-            ids_dev = ids_local.pin_memory().cuda(non_blocking=True)
+            dev = []
+            for t in parts:                              # pinned slices -> bucketed device buffers
+                if t is None:
+                    dev.append(None)
+                    continue
+                d = ops.empty_bucketed(t.shape[0], *t.shape[1:], dtype=t.dtype)
+                d.copy_(t, non_blocking=True)
+                dev.append(d)
+            ids_dev = self._ring.upload(ids_local.numpy())
             self.h2d_bytes_last = sum(t.numel() * t.element_size() for t in parts if t is not None) + ids_local.numel() * 8
         d_node_off, d_rowptr, d_col, d_x, d_y = dev
         max_nodes = int(self.h_n_nodes[ids].max()) if b else 0
         i32 = dict(dtype=torch.int32, device="cuda")
         graph_ptr, edge_ptr = torch.empty(b + 1, **i32), torch.empty(b + 1, **i32)
-        rowptr, colidx = torch.empty(n + 1, **i32), torch.empty(nnz, **i32)
-        x = torch.empty(n, self.n_feat, dtype=torch.float32, device="cuda")
-        seg = torch.empty(n, dtype=torch.int64, device="cuda")
+        rowptr, colidx = ops.empty_bucketed(n + 1, dtype=torch.int32), ops.empty_bucketed(nnz, dtype=torch.int32)
+        x = ops.empty_bucketed(n, self.n_feat, dtype=torch.float32)
+        seg = ops.empty_bucketed(n, dtype=torch.int64)
         y = torch.empty(b, self.n_classes, dtype=torch.float32, device="cuda") if (want_labels and d_y is not None) else None
-        coo = torch.empty(nnz, 2, dtype=torch.int64, device="cuda") if want_coo else None
+        coo = ops.empty_bucketed(nnz, 2, dtype=torch.int64) if want_coo else None
         flag = torch.zeros(1, **i32)
         # the uploaded slices are addressed with DATASET-global ids: rebase the pointers instead
         # of the index arrays (the kernel only touches [g0, g1], [n0, n1], [e0, e1))
@@ -465,6 +519,7 @@ class DisjointLoader:
         self._order = np.arange(self._n, dtype=np.int64)
         self._order_dev = None
         self._order_epoch = -1
+        self._ring = _PinnedRing(depth=4)
         self._generator = self._generate()
 
     @property
@@ -534,16 +589,15 @@ class DisjointLoader:
         torch = _lib.require_cuda()
         epoch, lo, hi, ids_host, global_count, order_host = item
         with torch.cuda.stream(stream):
+            # persistent pinned staging (see _PinnedRing: no pinned allocation inside the loop)
             if lo is None:                                     # work-balanced shard: its own id list
-                staged = torch.from_numpy(ids_host).pin_memory()
-                ids_dev = staged.cuda(non_blocking=True)
+                ids_dev = self._ring.upload(ids_host)
             else:
                 if self._order_epoch != epoch:                 # one upload of the epoch's permutation, then slices of it
-                    self._order_staged = torch.from_numpy(order_host).pin_memory()
-                    self._order_dev = self._order_staged.cuda(non_blocking=True)
+                    self._order_dev = self._ring.upload(order_host)
                     self._order_epoch = epoch
-                staged = self._order_staged                    # pinned buffers stay alive until their copy has run
                 ids_dev = self._order_dev[lo:hi]
+            staged = None
             x, a, i, y = self.store.batch(ids_dev, ids_host, want_coo=self.want_coo)
             a.global_batch_graphs = global_count
             a._ids_keepalive = (ids_dev, staged)

@@ -246,7 +246,7 @@ class GeneralGNN:
             raise RuntimeError("gcs_model_workspace_bytes failed: " + lib.gcs_last_error().decode())
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
-            self._ws = torch.empty(int(need * 1.05) + 256, dtype=torch.uint8, device="cuda")
+            self._ws = torch.empty(int(need * 1.08) + 256, dtype=torch.uint8, device="cuda")
         return self._ws
 
     def _rows_out(self, batch):

@@ -6,6 +6,8 @@ torch's current stream.  No arithmetic happens in Python.
 """
 from __future__ import annotations
 
+import numpy as np
+
 from typing import Optional, Tuple
 
 from . import _lib
@@ -46,9 +48,50 @@ def _vec(t, name, dtype=None, n=None):
     return t
 
 
+def empty_bucketed(n, *rest, dtype=None, zero=False):
+    """``torch.empty((n, *rest))`` on the device, carved out of an allocation whose leading dimension is rounded up to
+    1/16 .. 1/8 of its size.  The per-batch tensors of a training loop (rows, entries, features of a disjoint batch)
+    change size by a per cent or two from step to step; with exact sizes the caching allocator keeps meeting requests
+    it has no block for and falls through to ``cudaMalloc`` in the middle of the loop - measured: 5 ms on the launching
+    thread at the least, 25-75 ms now and then, with the GPU idle behind it.  Bucketed, every step after the first few
+    is served from the cache."""
+    torch = _t()
+    n = int(n)
+    pad = n
+    if n >= 4096:
+        g = 1 << (n.bit_length() - 4)
+        pad = (n + g - 1) // g * g
+    dtype = dtype or torch.float32
+    _reserve_spares(torch, pad * int(np.prod(rest, dtype=np.int64)) * torch.empty((), dtype=dtype).element_size())
+    make = torch.zeros if zero else torch.empty
+    return make((pad, *rest), dtype=dtype, device="cuda")[:n]
+
+
+_SPARES_SEEN = set()
+
+
+def _reserve_spares(torch, nbytes):
+    """The first time a block size is asked for, two more blocks of that size are allocated and released, and the pool
+    of small blocks (< 1 MB: row-block pointers, graph pointers, labels) is grown by a few segments once: how many
+    batch tensors of a size are alive at the same moment changes over the first steps (prefetch, an epoch boundary, a
+    batch the caller still holds), and the caching allocator answers 'one more block of this size' with a cudaMalloc -
+    5 ms on the launching thread when all goes well, 30-300 ms now and then on this pool's hosts (measured: one such
+    step in every third 10-step region of bench.py, always the first step of the second epoch, a 2 MB segment for the
+    small pool).  Afterwards the loop allocates nothing from the driver."""
+    if not _SPARES_SEEN:
+        _SPARES_SEEN.add(0)
+        warm = [torch.empty(900_000, dtype=torch.uint8, device="cuda") for _ in range(16)]
+        del warm
+    key = int(nbytes)
+    if key >= (1 << 20) and key not in _SPARES_SEEN:
+        _SPARES_SEEN.add(key)
+        spare = [torch.empty(key, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        del spare
+
+
 def _ws(nbytes):
     torch = _t()
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda")
+    return empty_bucketed(max(int(nbytes), 256), dtype=torch.uint8)
 
 
 def check_status_flag(flag, what):
@@ -105,9 +148,9 @@ def csr_transpose(rowptr, colidx):
     lib = _lib.load()
     n = rowptr.shape[0] - 1
     nnz = colidx.shape[0]
-    rp_t = torch.empty_like(rowptr)
-    ci_t = torch.empty_like(colidx)
-    ws = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    rp_t = empty_bucketed(n + 1, dtype=torch.int32)
+    ci_t = empty_bucketed(nnz, dtype=torch.int32)
+    ws = empty_bucketed(n + 1, dtype=torch.int32)
     check(lib.gcs_csr_transpose(ptr(rowptr), ptr(colidx), n, nnz, ptr(rp_t), ptr(ci_t), ptr(ws), stream_ptr()),
           "gcs_csr_transpose")
     return rp_t, ci_t
@@ -251,8 +294,8 @@ def build_rb(rowptr, colidx, height: int = 4):
     n = rowptr.shape[0] - 1
     nnz = colidx.shape[0]
     n_blk = (n + height - 1) // height
-    blk_ptr = torch.zeros(n_blk + 4, dtype=torch.int32, device="cuda")[:n_blk + 1]    # 3 words of slack: read in 16-byte units
-    ent = torch.empty(max(nnz + 3 * ((n + height - 1) // height), 4), dtype=torch.int32, device="cuda")   # blocks are padded to 4 entries
+    blk_ptr = empty_bucketed(n_blk + 4, dtype=torch.int32, zero=True)[:n_blk + 1]    # 3 words of slack: read in 16-byte units
+    ent = empty_bucketed(max(nnz + 3 * ((n + height - 1) // height), 4), dtype=torch.int32)   # blocks are padded to 4 entries
     ws = _ws(lib.gcs_spmm_rb_workspace_bytes(n, height))
     check(lib.gcs_spmm_build_rb(ptr(rowptr), ptr(colidx), n, nnz, height, ptr(blk_ptr), ptr(ent), ptr(ws), ws.numel(),
                                 stream_ptr()), "gcs_spmm_build_rb")
