@@ -165,17 +165,21 @@ int gcs_bn_prelu_bwd(const float* da, int64_t ldda, const float* h, int64_t ldh,
  * tf.math.unsorted_segment_sum, the messages never materialised).  f is the fused
  * BatchNorm+PReLU prologue of GeneralConv.call, f(x) = prelu(x*scale + shift, alpha);
  * pass scale = shift = alpha = NULL for f = identity (that is also the backward:
- * dX = pattern(A)^T . dY, called with the transposed CSR).  Neighbours are accumulated in
- * ascending column order per output row.
+ * dX = pattern(A)^T . dY, called with the transposed CSR).  Every output element has one owner that adds its
+ * neighbours in a fixed order (no atomics): ascending column for the CSR row kernels, the order of the row-block list
+ * for the row-block kernels - results are reproducible run to run and differ between the two families only by the
+ * float32 rounding of a reordered sum (~1e-7).
  * Row-block format (optional): gcs_spmm_build_rb derives, once per batch, the row-block form of the CSR: per block of
- * rb_height (2 or 4) consecutive rows the sorted union of their columns, each entry (col << 8) | mask-of-rows.  Banded
+ * rb_height (2 or 4) consecutive rows the union of their columns, each entry (col << 8) | mask-of-rows.  Banded
  * residue graphs share most neighbours between consecutive rows, so a neighbour row is gathered once per block instead
- * of once per row.  Every block is padded to a multiple of 4 entries (mask 0: no-ops) so that it starts on a 16-byte
- * boundary.  rb_blk_ptr needs ceil(n_rows/rb_height)+1 int32 (allocate 3 more: gcs_spmm_sum_graphs copies it in
+ * of once per row.  Order inside a block: first whole groups of four entries that ALL rows of the block have (mask all
+ * ones, ascending column, bit 4 of the word set: a kernel may sum them once for the whole block), then every other
+ * entry in ascending column order.  Every block is padded to a multiple of 4 entries (mask 0: no-ops) so that it starts
+ * on a 16-byte boundary.  rb_blk_ptr needs ceil(n_rows/rb_height)+1 int32 (allocate 3 more: gcs_spmm_sum_graphs copies it in
  * 16-byte units), rb_ent nnz + 3*ceil(n_rows/rb_height) uint32 (upper bound); both 16-byte aligned; workspace
  * gcs_spmm_rb_workspace_bytes(n_rows, rb_height); n_rows < 2^24.  gcs_spmm_build_rb4 = height 4 (the only height the
- * global-memory kernel behind gcs_spmm_sum / gcs_spmm_aggregate reads).  With rb_* == NULL the CSR row kernels run;
- * results are bit-identical.  Any matrix structure is accepted either way.
+ * global-memory kernel behind gcs_spmm_sum / gcs_spmm_aggregate reads).  With rb_* == NULL the CSR row kernels run.
+ * Any matrix structure is accepted either way.
  * --------------------------------------------------------------------------------- */
 int64_t gcs_spmm_rb_workspace_bytes(int64_t n_rows, int32_t rb_height);
 int gcs_spmm_build_rb(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t nnz, int32_t rb_height,
@@ -196,7 +200,9 @@ int gcs_spmm_sum(const int32_t* rowptr, const int32_t* colidx, const int32_t* rb
  * per element - and serves all gathers of the graph from there.  max_graph_nodes = the longest graph of the batch
  * (the loader knows it on the host; 0 = unknown).  Batches whose graphs do not fit a shared-memory slab (or
  * graph_ptr == NULL, or rb_* == NULL) run on the global-memory kernels of gcs_spmm_aggregate.  An entry that leaves its graph's column
- * range is ignored (a caller error).  rb_* / rb_height as above; residual as in gcs_spmm_aggregate.  Results are bit-identical to gcs_spmm_sum. */
+ * range is ignored (a caller error).  rb_* / rb_height as above; residual as in gcs_spmm_aggregate.  Results are bit-identical to
+ * gcs_spmm_sum on the same row-block list.  Work items are handed to the persistent thread blocks through a ticket counter in
+ * device memory that the kernel re-arms itself (up to 64 launches of one device may be in flight at once). */
 int64_t gcs_spmm_slab_stage_bytes(void); /* bytes of one shared-memory stage: a graph runs 4 << k columns wide when
                                             n_nodes * (16 << k) + its row-block entries fit; the slab kernel takes a batch
                                             when max_graph_nodes * 16 and (n_rows / n_graphs) * 64 are both <= this */
