@@ -754,3 +754,60 @@ def test_sync_batchnorm_two_ranks_equal_one_step_on_the_union(small_case):
     x, a, seg, y = g.data.DeviceGraphStore(ds).batch(torch.from_numpy(ids).cuda(), ids)
     plain.train_step_grads([x, a, seg], y, grad_scale=1.0 / 8)
     assert rel_err(host(plain.state), ref["new_state"]) > 1e-4
+
+
+@pytest.mark.gpu
+def test_fused_step_with_weights_split_ahead_equals_forward_plus_backward():
+    """gcs_model_train_step splits the weight operands of all its tensor-core GEMMs in two launches at the start of the
+    step (model.cu: prepare_step_weights); the GradientTape route (gcs_model_forward + gcs_model_backward) lets every GEMM
+    prepare its own operand.  Same kernels, same split values: gradients, loss and BatchNorm state agree bit for bit."""
+    ds = synthetic.make_dataset(6, seed=11, n_mean=90, deg=10, n_feat=16)
+    (x, a, i), y = next(g.DisjointLoader(ds, batch_size=6, epochs=1, shuffle=False))
+    models = []
+    for _ in range(2):
+        m = g.GeneralGNN(2, activation="softmax", hidden=128, message_passing=3, seed=0)
+        m.build(16)
+        w, s = g.init_params(m.cfg, seed=5, perturb=True)
+        m.load_flat(w, s)
+        models.append(m)
+    fused, taped = models
+    loss_acc, probs = fused.train_step_grads((x, a, i), y)
+    with g.GradientTape() as tape:
+        pred = taped((x, a, i), training=True)
+        loss = g.CategoricalCrossentropy()(y, pred)
+    tape.gradient(loss, taped.trainable_variables)
+    assert torch.equal(probs, pred)
+    assert torch.equal(fused.grads, taped.grads)
+    assert torch.equal(fused.state, taped.state)
+    assert abs(float(loss) - float(host(loss_acc)[0])) < 1e-6
+
+
+@pytest.mark.gpu
+def test_batch_tensors_are_bucketed_and_a_running_loop_allocates_nothing():
+    """ops.empty_bucketed: sizes that differ by a per cent share one allocation size; a loader + train loop reaches the
+    driver's allocator in its first steps only (a cudaMalloc inside a step stalls the launching thread for milliseconds
+    to hundreds of milliseconds)."""
+    from gcn_string_b200 import ops
+    t1, t2 = ops.empty_bucketed(500_000, 8), ops.empty_bucketed(507_000, 8)
+    assert t1.shape == (500_000, 8) and t1.is_contiguous() and t2.shape == (507_000, 8)
+    assert t1.untyped_storage().nbytes() == t2.untyped_storage().nbytes() >= 507_000 * 8 * 4
+    small = ops.empty_bucketed(100, dtype=torch.int32, zero=True)
+    assert small.shape == (100,) and int(small.abs().sum()) == 0
+    ds = synthetic.make_dataset(96, seed=3, n_mean=120, deg=10, n_feat=16)
+    model = g.GeneralGNN(2, activation="softmax", hidden=64, message_passing=2, seed=0)
+    model.build(16)
+    loader = g.DisjointLoader(ds, batch_size=24, epochs=None, shuffle=True)
+    opt = g.optimizers.SGD(learning_rate=0.01)
+
+    def step():
+        (x, a, i), y = next(loader)
+        model.train_step_grads((x, a, i), y)
+        opt.apply_flat(model.params, model.grads)
+    for _ in range(16):                                   # four epochs: every batch composition bucket has been seen
+        step()
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_stats().get("num_device_alloc", 0)
+    for _ in range(24):
+        step()
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_stats().get("num_device_alloc", 0) == before
