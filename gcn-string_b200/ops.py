@@ -62,7 +62,7 @@ def empty_bucketed(n, *rest, dtype=None, zero=False):
         g = 1 << (n.bit_length() - 4)
         pad = (n + g - 1) // g * g
     dtype = dtype or torch.float32
-    _reserve_spares(torch, pad * int(np.prod(rest, dtype=np.int64)) * torch.empty((), dtype=dtype).element_size())
+    _reserve_spares(torch, pad * int(np.prod(rest, dtype=np.int64)) * dtype.itemsize)
     make = torch.zeros if zero else torch.empty
     return make((pad, *rest), dtype=dtype, device="cuda")[:n]
 
@@ -71,21 +71,22 @@ _SPARES_SEEN = set()
 
 
 def _reserve_spares(torch, nbytes):
-    """The first time a block size is asked for, two more blocks of that size are allocated and released, and the pool
+    """The first time a block size is asked for, three more blocks of that size are allocated and released, and the pool
     of small blocks (< 1 MB: row-block pointers, graph pointers, labels) is grown by a few segments once: how many
     batch tensors of a size are alive at the same moment changes over the first steps (prefetch, an epoch boundary, a
     batch the caller still holds), and the caching allocator answers 'one more block of this size' with a cudaMalloc -
     5 ms on the launching thread when all goes well, 30-300 ms now and then on this pool's hosts (measured: one such
     step in every third 10-step region of bench.py, always the first step of the second epoch, a 2 MB segment for the
     small pool).  Afterwards the loop allocates nothing from the driver."""
-    if not _SPARES_SEEN:
-        _SPARES_SEEN.add(0)
+    dev = torch.cuda.current_device()
+    if (dev, 0) not in _SPARES_SEEN:
+        _SPARES_SEEN.add((dev, 0))
         warm = [torch.empty(900_000, dtype=torch.uint8, device="cuda") for _ in range(16)]
         del warm
-    key = int(nbytes)
-    if key >= (1 << 20) and key not in _SPARES_SEEN:
+    key = (dev, int(nbytes))
+    if (1 << 20) <= key[1] <= (1 << 28) and key not in _SPARES_SEEN:      # 1 MB .. 256 MB: the per-batch tensors
         _SPARES_SEEN.add(key)
-        spare = [torch.empty(key, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        spare = [torch.empty(key[1], dtype=torch.uint8, device="cuda") for _ in range(3)]
         del spare
 
 
