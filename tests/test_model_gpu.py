@@ -796,14 +796,16 @@ def test_batch_tensors_are_bucketed_and_a_running_loop_allocates_nothing():
     ds = synthetic.make_dataset(96, seed=3, n_mean=120, deg=10, n_feat=16)
     model = g.GeneralGNN(2, activation="softmax", hidden=64, message_passing=2, seed=0)
     model.build(16)
-    loader = g.DisjointLoader(ds, batch_size=24, epochs=None, shuffle=True)
+    # four batches of different sizes, epoch after epoch (no reshuffling: the sequence of sizes - and with it whether the
+    # model workspace ever has to grow - does not depend on the state of NumPy's global generator)
+    loader = g.DisjointLoader(ds, batch_size=24, epochs=None, shuffle=False)
     opt = g.optimizers.SGD(learning_rate=0.01)
 
     def step():
         (x, a, i), y = next(loader)
         model.train_step_grads((x, a, i), y)
         opt.apply_flat(model.params, model.grads)
-    for _ in range(16):                                   # four epochs: every batch composition bucket has been seen
+    for _ in range(16):                                   # four epochs: every batch size has been seen
         step()
     torch.cuda.synchronize()
     before = torch.cuda.memory_stats().get("num_device_alloc", 0)
