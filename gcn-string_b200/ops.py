@@ -48,6 +48,16 @@ def _vec(t, name, dtype=None, n=None):
     return t
 
 
+def bucket_rows(n: int) -> int:
+    """Leading dimension actually allocated for ``n`` rows: ``n`` itself below 4096, otherwise ``n`` rounded up to a
+    multiple of 2**(bit_length(n) - 4), i.e. to 1/16 .. 1/8 of itself (at most 12.5 % more than asked for)."""
+    n = int(n)
+    if n < 4096:
+        return n
+    g = 1 << (n.bit_length() - 4)
+    return (n + g - 1) // g * g
+
+
 def empty_bucketed(n, *rest, dtype=None, zero=False):
     """``torch.empty((n, *rest))`` on the device, carved out of an allocation whose leading dimension is rounded up to
     1/16 .. 1/8 of its size.  The per-batch tensors of a training loop (rows, entries, features of a disjoint batch)
@@ -57,10 +67,7 @@ def empty_bucketed(n, *rest, dtype=None, zero=False):
     is served from the cache."""
     torch = _t()
     n = int(n)
-    pad = n
-    if n >= 4096:
-        g = 1 << (n.bit_length() - 4)
-        pad = (n + g - 1) // g * g
+    pad = bucket_rows(n)
     dtype = dtype or torch.float32
     _reserve_spares(torch, pad * int(np.prod(rest, dtype=np.int64)) * dtype.itemsize)
     make = torch.zeros if zero else torch.empty

@@ -129,3 +129,18 @@ def test_roc_curve_and_auc_match_scikit_learn(seed, n, ties):
         auc([0.0, 1.0, 0.5], [0.0, 1.0, 1.0])
     with pytest.raises(ValueError):
         auc([0.0], [1.0])
+
+
+def test_bucketed_batch_tensor_sizes():
+    """ops.bucket_rows (the allocation size behind every per-batch tensor): never less than asked for, at most 12.5 % more,
+    and sizes that differ by a per cent or two - consecutive batches of a loader - share one bucket almost always."""
+    from gcn_string_b200.ops import bucket_rows
+    rng = np.random.default_rng(0)
+    for n in [0, 1, 4095, 4096, 4097, 508180, 6120690, 2**24 - 1] + rng.integers(1, 10**8, 200).tolist():
+        b = bucket_rows(n)
+        assert b >= n and (n < 4096 and b == n or b <= n * 1.125 + 1)
+        assert bucket_rows(b) == b                                   # a bucket boundary maps to itself
+    sizes = (508180 * (1 + 0.008 * rng.standard_normal(2000))).astype(np.int64)      # cfg2: rows of a batch, +-0.8 %
+    assert len({bucket_rows(int(v)) for v in sizes}) <= 2
+    nnz = (6120690 * (1 + 0.008 * rng.standard_normal(2000))).astype(np.int64)
+    assert len({bucket_rows(int(v)) for v in nnz}) <= 2
